@@ -1,0 +1,37 @@
+"""pytest configuration: registers the `gpu` marker and shared fixtures.
+
+`-m "not gpu"` runs here on CPU (oracle vs golden vectors, host logic, C-ABI symbol export, gloo world_size-2);
+`-m gpu` runs on a B200 and calls the CUDA path through the C-ABI.
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(params=golden_names())
+def golden(request):
+    case = load_golden(request.param)
+    case["name"] = request.param
+    return case
