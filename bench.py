@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- MSDeformAttn hot-path benchmark (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # the reference's CPU path (torch port) on host cores
+
+One *step* = one pass of the hot path over one batch of the workload (default cfg2 = BASELINE.json configs[1]:
+COCO-shape 1333x800, R50 4-level features, 300 queries, 8 heads x 32, 4 levels x 4 points, batch 2, fp32): the
+6 encoder-shaped + 6 decoder-shaped MSDeformAttn calls of one transformer pass, each forward AND backward,
+through the reference-facing module functions (``MultiScaleDeformableAttention.ms_deform_attn_forward/backward``
+-> C ABI).  Every call has its own input tensors (12 distinct sets, ~1 GB > the 126 MB L2), so nothing is served
+from a warm cache between steps.
+
+Reported (one JSON line, rank 0):
+  value      -- Gsamples/s, whole job (all ranks), device-resident inputs; a sample = one bilinear D-vector tap
+                (N*Lq*M*L*P per call), counted once per forward+backward pair.
+  e2e        -- same metric with HOST (pinned) inputs and results: H2D of value/loc/attn/grad_out and D2H of
+                out/grad_value/grad_loc/grad_attn inside the timed region.
+  roofline   -- dominant kernel (encoder-shaped backward: memset + msda_bwd_tiled) against the measured HBM peak.
+  cpu_baseline -- torch port of the reference's ms_deform_attn_core_pytorch CPU path on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from uninext_b200.workloads import CONFIGS, algorithmic_bytes, make_inputs  # noqa: E402
+
+METRIC = "msdeformattn_fwd_bwd_gsamples_per_s"
+UNIT = "Gsamples/s"
+N_ENC, N_DEC = 6, 6        # op calls per transformer pass (deformable_transformer.py: 6 encoder + 6 decoder layers)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="target CPU seconds for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for ln in self.proc.stdout:
+                self.lines.append(ln.strip())
+        self.thr = threading.Thread(target=pump, daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_calls(cfg, device, dtype, seed0):
+    """12 distinct input sets: 6 encoder-shaped (Lq = S) + 6 decoder-shaped (Lq = dec queries)."""
+    calls = []
+    for i in range(N_ENC):
+        d = make_inputs(cfg, "enc", device, dtype=dtype, seed=seed0 + i)
+        d["kind"] = "enc"
+        calls.append(d)
+    for i in range(N_DEC):
+        d = make_inputs(cfg, "dec", device, dtype=dtype, seed=seed0 + 100 + i)
+        d["kind"] = "dec"
+        calls.append(d)
+    return calls
+
+
+def samples_per_step(cfg):
+    return N_ENC * cfg.samples("enc") + N_DEC * cfg.samples("dec")
+
+
+def run_b200(args):
+    from uninext_b200 import _cabi
+    from uninext_b200.dropin import MultiScaleDeformableAttention as MSDA
+
+    world, rank, local = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    lib = _cabi.load()
+    cfg = CONFIGS[args.config]
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    elem = 4 if args.dtype == "fp32" else 2
+    calls = build_calls(cfg, device, dtype, seed0=1000 * rank)
+    smp_step = samples_per_step(cfg)
+
+    def op_args(c):
+        return (c["value"], c["spatial_shapes"], c["level_start_index"], c["sampling_locations"],
+                c["attention_weights"])
+
+    def step(ev=None):
+        for i, c in enumerate(calls):
+            a = op_args(c)
+            if ev is not None:
+                ev[i][0].record()
+            out = MSDA.ms_deform_attn_forward(*a, 64)
+            if ev is not None:
+                ev[i][1].record()
+            grads = MSDA.ms_deform_attn_backward(*a, c["grad_output"], 64)
+            if ev is not None:
+                ev[i][2].record()
+        return out, grads
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-resident inputs ----
+    K = args.steps
+    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in calls] for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = lib.msda_launch_count()
+    t0.record()
+    for k in range(K):
+        step(evs[k])
+    t1.record()
+    barrier()
+    launches = lib.msda_launch_count() - launches0
+    total_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * smp_step / (ms_per_step * 1e-3) / 1e9
+
+    # per-kernel durations (events on the launching stream), averaged over the timed region
+    def avg(kind, a, b):
+        xs = [evs[k][i][a].elapsed_time(evs[k][i][b]) for k in range(K) for i, c in enumerate(calls) if c["kind"] == kind]
+        return sum(xs) / len(xs)
+    kern = {"enc_fwd_ms": avg("enc", 0, 1), "enc_bwd_ms": avg("enc", 1, 2),
+            "dec_fwd_ms": avg("dec", 0, 1), "dec_bwd_ms": avg("dec", 1, 2)}
+    peak, peak_src = measured_peaks()
+    b_bwd = algorithmic_bytes(cfg, "enc", elem, "bwd")
+    b_fwd = algorithmic_bytes(cfg, "enc", elem, "fwd")
+    ach = b_bwd / (kern["enc_bwd_ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "encoder-shaped backward: cudaMemsetAsync(grad_value) + msda_bwd_tiled",
+                "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": b_bwd, "traffic": None,
+                "enc_fwd": {"achieved": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9, 1),
+                            "frac": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9 / peak, 4),
+                            "algorithmic_bytes_per_launch": b_fwd}}
+
+    # ---- e2e: host (pinned) buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(MSDA, calls, op_args, world, smp_step, args.e2e_steps, device, barrier)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(cfg, args.cpu_budget_s)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": cfg.name, "levels": cfg.shapes, "S": cfg.S, "frames_per_gpu": cfg.batch,
+                       "heads": cfg.heads, "head_dim": cfg.head_dim, "points": cfg.points,
+                       "dec_queries": cfg.dec_queries, "calls_per_step": f"{N_ENC} enc + {N_DEC} dec, fwd+bwd",
+                       "samples_per_step_per_gpu": smp_step, "parallelism": f"dp{world} (frames sharded, no exchange)",
+                       "l2_policy": "12 distinct input sets per step (~1 GB) > 126 MB L2"},
+            "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+            "gsamples_per_s": {"enc_fwd": round(cfg.samples("enc") / kern["enc_fwd_ms"] / 1e6, 2),
+                               "enc_bwd": round(cfg.samples("enc") / kern["enc_bwd_ms"] / 1e6, 2),
+                               "dec_fwd": round(cfg.samples("dec") / kern["dec_fwd_ms"] / 1e6, 2),
+                               "dec_bwd": round(cfg.samples("dec") / kern["dec_bwd_ms"] / 1e6, 2)},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_e2e(MSDA, calls, op_args, world, smp_step, steps, device, barrier):
+    """Same step, but inputs start in pinned host memory and results end there."""
+    host_in, host_out, dev_in = [], [], []
+    h2d = d2h = 0
+    for c in calls:
+        hin = {k: c[k].cpu().pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
+        host_in.append(hin)
+        dev_in.append({k: torch.empty_like(c[k]) for k in hin})
+        h2d += sum(t.numel() * t.element_size() for t in hin.values())
+        n, lq = c["sampling_locations"].shape[:2]
+        res = {"out": torch.empty((n, lq, c["value"].shape[2] * c["value"].shape[3]), dtype=c["value"].dtype).pin_memory(),
+               "grad_value": torch.empty(c["value"].shape, dtype=c["value"].dtype).pin_memory(),
+               "grad_loc": torch.empty(c["sampling_locations"].shape, dtype=c["sampling_locations"].dtype).pin_memory(),
+               "grad_attn": torch.empty(c["attention_weights"].shape, dtype=c["attention_weights"].dtype).pin_memory()}
+        host_out.append(res)
+        d2h += sum(t.numel() * t.element_size() for t in res.values())
+
+    def e2e_step():
+        for c, hin, din, res in zip(calls, host_in, dev_in, host_out):
+            for k in hin:
+                din[k].copy_(hin[k], non_blocking=True)
+            a = (din["value"], c["spatial_shapes"], c["level_start_index"], din["sampling_locations"],
+                 din["attention_weights"])
+            out = MSDA.ms_deform_attn_forward(*a, 64)
+            gv, gl, ga = MSDA.ms_deform_attn_backward(*a, din["grad_output"], 64)
+            res["out"].copy_(out, non_blocking=True)
+            res["grad_value"].copy_(gv, non_blocking=True)
+            res["grad_loc"].copy_(gl, non_blocking=True)
+            res["grad_attn"].copy_(ga, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= steps
+    return {"value": round(world * smp_step / (ms * 1e-3) / 1e9, 4), "unit": UNIT, "ms_per_step": round(ms, 3),
+            "steps": steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "MultiScaleDeformableAttention.ms_deform_attn_forward/backward on pinned-host inputs"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs: the reference's CPU path (torch port of ms_deform_attn_core_pytorch; oracle/ is test infrastructure and
+# is imported here ONLY as the measured baseline, never by the product path).
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_call(port, c):
+    v = c["value"].clone().requires_grad_(True)
+    lo = c["sampling_locations"].clone().requires_grad_(True)
+    at = c["attention_weights"].clone().requires_grad_(True)
+    out = port(v, c["spatial_shapes"], lo, at)
+    out.backward(c["grad_output"])
+    return out
+
+
+def cpu_sample_calls(cfg, frames):
+    """One encoder-shaped + one decoder-shaped call on `frames` frames (a 1/6 slice of a step at full batch)."""
+    import dataclasses
+    sub = dataclasses.replace(cfg, batch=frames)
+    return [make_inputs(sub, "enc", "cpu", seed=1), make_inputs(sub, "dec", "cpu", seed=2)], \
+        sub.samples("enc") + sub.samples("dec")
+
+
+def cpu_baseline(cfg, budget_s):
+    from oracle.msda_oracle import core_pytorch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    calls, smp = cpu_sample_calls(cfg, cfg.batch)
+    t = time.perf_counter()
+    for c in calls:
+        cpu_call(core_pytorch_port, c)                 # warm-up + probe
+    probe = time.perf_counter() - t
+    reps = max(1, min(10, int(budget_s / max(probe, 1e-3)) - 1))
+    t = time.perf_counter()
+    for _ in range(reps):
+        for c in calls:
+            cpu_call(core_pytorch_port, c)
+    dt = (time.perf_counter() - t) / reps
+    return {"value": round(smp / dt / 1e9, 5), "unit": UNIT, "cores": cores, "kind": "port",
+            "impl": "torch port of ms_deform_attn_core_pytorch (grid_sample per level) fwd + autograd bwd",
+            "sample": f"{reps} x (1 encoder-shaped + 1 decoder-shaped call, {cfg.batch} frames, fwd+bwd) = 1/6 of a step",
+            "seconds_per_sample": round(dt, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same metric."""
+    world, rank, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle.msda_oracle import core_pytorch_port
+    cfg = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample per step: 1 enc + 1 dec call; shrink to 1 frame if a step would take > ~6 s
+    calls, smp = cpu_sample_calls(cfg, cfg.batch)
+    t = time.perf_counter()
+    for c in calls:
+        cpu_call(core_pytorch_port, c)
+    probe = time.perf_counter() - t
+    frames = cfg.batch
+    if probe * (args.steps + args.warmup) > 240 and cfg.batch > 1:
+        frames = 1
+        calls, smp = cpu_sample_calls(cfg, 1)
+    for _ in range(max(0, args.warmup - 1)):
+        for c in calls:
+            cpu_call(core_pytorch_port, c)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        for c in calls:
+            cpu_call(core_pytorch_port, c)
+    dt = (time.perf_counter() - t) / args.steps
+    val = round(smp / dt / 1e9, 5)
+    sample = f"per step: 1 encoder-shaped + 1 decoder-shaped call on {frames} frame(s), fwd + autograd bwd"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.name, "levels": cfg.shapes, "S": cfg.S, "frames_per_gpu": cfg.batch,
+                   "heads": cfg.heads, "head_dim": cfg.head_dim, "points": cfg.points, "dec_queries": cfg.dec_queries},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "impl": "torch port of the reference's ms_deform_attn_core_pytorch (the reference file cannot "
+                                 "travel to the GPU box; the port is pinned to it by tests/golden)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

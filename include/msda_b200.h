@@ -1,0 +1,97 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention library (libmsda_b200.so).
+ *
+ * This is the drop-in boundary for the reference's native module `MultiScaleDeformableAttention`
+ * (projects/UNINEXT/uninext/models/deformable_detr/ops/src/vision.cpp:13-16), whose two functions
+ *     ms_deform_attn_forward  (ops/src/ms_deform_attn.h:19-39  -> ops/src/cuda/ms_deform_attn_cuda.cu:20-80)
+ *     ms_deform_attn_backward (ops/src/ms_deform_attn.h:41-62  -> ops/src/cuda/ms_deform_attn_cuda.cu:83-153)
+ * take ATen tensors. Here the same work is exposed with plain pointers and sizes; no torch / ATen type crosses
+ * this interface. The reference-side binding (a 40-line pybind or ctypes shim) is shown in INTEGRATION.md and
+ * shipped as uninext_b200/dropin/MultiScaleDeformableAttention.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device, 16-byte aligned, dense row-major:
+ *       value              [N, S, M, D]          (reference: ms_deform_attn_cuda.cu:40-43)
+ *       spatial_shapes     [L, 2] int64 (H_l,W_l)  -- read on the device, no host sync (cu:67)
+ *       level_start_index  [L]    int64            (cu:68)
+ *       sampling_loc       [N, Lq, M, L, P, 2]   last dim (x, y) in [0,1] of the level map (cu:69)
+ *       attn_weight        [N, Lq, M, L, P]      (cu:70)
+ *       out / grad_out     [N, Lq, M*D]          (cu:54,77)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Calls are asynchronous with
+ *     respect to the host, stateless and re-entrant (reference: at::cuda::getCurrentCUDAStream(), cu:65,135).
+ *   - return value: 0 on success; a positive cudaError_t if a CUDA call or kernel launch failed (the reference
+ *     only printf()s these, ms_deform_im2col_cuda.cuh:948-952,1321-1325 -- here they are returned);
+ *     a negative MSDA_E_* for argument errors. msda_strerror() renders either.
+ *   - there is no im2col_step: the reference chunks the batch only to bound its int32 indexing and temporary
+ *     sizes (cu:50-52,61-75); these kernels use 64-bit offsets and take the whole batch in one launch. The
+ *     Python shim still validates `batch % min(batch, im2col_step) == 0` like the reference (cu:52).
+ *   - the *_bf16 entry points are new (the reference dispatches float/double only, cu:64,134): value, out and
+ *     grad_out are bfloat16 bit patterns (uint16_t), sampling_loc / attn_weight and their gradients stay fp32,
+ *     accumulation is fp32.
+ *   - backward: grad_value is zero-filled by the callee (the reference's at::zeros_like, cu:121); grad_sampling_loc
+ *     and grad_attn_weight are fully overwritten. grad_value accumulation order is not deterministic (fp32 atomics),
+ *     like the reference.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+#define MSDA_E_BADARG   (-1)   /* null pointer, non-positive dimension, misaligned pointer            */
+#define MSDA_E_TOOLARGE (-2)   /* a dimension product exceeds what the kernels index (see msda_b200.h) */
+#define MSDA_E_NODEVICE (-3)   /* no sm_100 device is current                                          */
+
+int msda_abi_version(void);
+const char *msda_strerror(int code);
+
+/* Which kernel family a (dtype, D, L, P) problem is routed to: 1 = tiled sm_100a fast path, 0 = generic.
+ * dtype_bytes: 2 (bf16), 4 (fp32), 8 (fp64). Used by the tests to prove the fast path is the one exercised. */
+int msda_uses_fast_path(int dtype_bytes, int D, int L, int P);
+
+/* Number of kernel launches (memsets excluded) this process has issued through this library. */
+uint64_t msda_launch_count(void);
+
+/* ---- forward: replaces ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80) ---- */
+int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const float *sampling_loc, const float *attn_weight,
+                     int N, int S, int M, int D, int L, int Lq, int P,
+                     float *out, void *stream);
+int msda_forward_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const double *sampling_loc, const double *attn_weight,
+                     int N, int S, int M, int D, int L, int Lq, int P,
+                     double *out, void *stream);
+int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *sampling_loc, const float *attn_weight,
+                      int N, int S, int M, int D, int L, int Lq, int P,
+                      uint16_t *out, void *stream);
+
+/* ---- backward: replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:83-153) ---- */
+int msda_backward_f32(const float *grad_out, const float *value,
+                      const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *sampling_loc, const float *attn_weight,
+                      int N, int S, int M, int D, int L, int Lq, int P,
+                      float *grad_value, float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+int msda_backward_f64(const double *grad_out, const double *value,
+                      const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const double *sampling_loc, const double *attn_weight,
+                      int N, int S, int M, int D, int L, int Lq, int P,
+                      double *grad_value, double *grad_sampling_loc, double *grad_attn_weight, void *stream);
+/* bf16 backward accumulates grad_value in fp32: `grad_value_f32` [N,S,M,D] fp32 is the accumulator (zero-filled by
+ * the callee) and `grad_value` receives its bf16 rounding. Pass grad_value == NULL to keep only the fp32 result. */
+int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value,
+                       const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const float *sampling_loc, const float *attn_weight,
+                       int N, int S, int M, int D, int L, int Lq, int P,
+                       float *grad_value_f32, uint16_t *grad_value,
+                       float *grad_sampling_loc, float *grad_attn_weight, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

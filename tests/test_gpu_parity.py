@@ -1,0 +1,323 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI by the drop-in module,
+against (1) the golden vectors produced by the reference's own ms_deform_attn_core_pytorch, (2) the CPU oracle on
+seeded inputs, (3) size-independent identities at BASELINE.json's full sizes, and (4) the reference's own
+ops/test.py checks (fwd fp64 / fwd fp32 / fp64 gradcheck over its channel list) turned into asserts.
+
+Tolerances (north_star): 1e-4 relative-to-scale for fp32, 1e-2 for bf16; fp64 near machine precision.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_oracle
+from tests.conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from uninext_b200 import _cabi
+    from uninext_b200.dropin import MultiScaleDeformableAttention as MSDA
+    from uninext_b200.functions import MSDeformAttnFunction, MSDeformAttnFunctionBF16
+    from uninext_b200.workloads import CONFIGS, OpConfig, make_inputs
+
+DEV = "cuda"
+
+
+def _to_dev(case, dtype):
+    aux = torch.float64 if dtype == torch.float64 else torch.float32
+    t = lambda k, dt: torch.from_numpy(case[k]).to(DEV, dt).contiguous()
+    return (t("value", dtype), t("spatial_shapes", torch.int64), t("level_start_index", torch.int64),
+            t("sampling_locations", aux), t("attention_weights", aux))
+
+
+def _scale(a):
+    return max(1e-30, float(np.abs(a).max()))
+
+
+def _maxerr(got, want):
+    return float(np.abs(got.astype(np.float64) - want).max()) / _scale(want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (1) golden vectors from the reference
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp64(name):
+    c = load_golden(name)
+    args = _to_dev(c, torch.float64)
+    out = MSDA.ms_deform_attn_forward(*args, 64)
+    assert _maxerr(out.cpu().numpy(), c["out"]) < 1e-12
+    go = torch.from_numpy(c["grad_output"]).to(DEV)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*args, go, 64)
+    assert _maxerr(gv.cpu().numpy(), c["grad_value"]) < 1e-11
+    assert _maxerr(gl.cpu().numpy(), c["grad_sampling_locations"]) < 1e-10
+    assert _maxerr(ga.cpu().numpy(), c["grad_attention_weights"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp32(name):
+    c = load_golden(name)
+    args = _to_dev(c, torch.float32)
+    out = MSDA.ms_deform_attn_forward(*args, 64)
+    assert _maxerr(out.cpu().numpy(), c["out"]) < 1e-4
+    go = torch.from_numpy(c["grad_output"]).to(DEV, torch.float32)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*args, go, 64)
+    assert _maxerr(gv.cpu().numpy(), c["grad_value"]) < 1e-4
+    assert _maxerr(gl.cpu().numpy(), c["grad_sampling_locations"]) < 1e-4
+    assert _maxerr(ga.cpu().numpy(), c["grad_attention_weights"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["prod_small", "prod_small_wide", "prod_small_edges", "d64"])
+def test_golden_bf16(name):
+    c = load_golden(name)
+    v, ss, lsi, loc, attn = _to_dev(c, torch.bfloat16)
+    assert _cabi.load().msda_uses_fast_path(2, v.shape[3], ss.shape[0], loc.shape[4]) == 1
+    out = MSDA.ms_deform_attn_forward(v, ss, lsi, loc, attn, 64)
+    assert out.dtype == torch.bfloat16
+    assert _maxerr(out.float().cpu().numpy(), c["out"]) < 1e-2
+    go = torch.from_numpy(c["grad_output"]).to(DEV, torch.bfloat16)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, ss, lsi, loc, attn, go, 64)
+    assert gv.dtype == torch.bfloat16 and gl.dtype == torch.float32
+    assert _maxerr(gv.float().cpu().numpy(), c["grad_value"]) < 1e-2
+    assert _maxerr(gl.cpu().numpy(), c["grad_sampling_locations"]) < 2e-2
+    assert _maxerr(ga.cpu().numpy(), c["grad_attention_weights"]) < 1e-2
+
+
+def test_production_shapes_use_fast_path():
+    lib = _cabi.load()
+    assert lib.msda_uses_fast_path(4, 32, 4, 4) == 1 and lib.msda_uses_fast_path(2, 32, 4, 4) == 1
+    assert lib.msda_uses_fast_path(8, 32, 4, 4) == 0 and lib.msda_uses_fast_path(4, 30, 2, 2) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (2) seeded inputs vs the CPU oracle (fp64 truth), incl. out-of-range taps
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_truth(inp):
+    f64 = lambda t: t.detach().double().cpu().numpy()
+    args = (f64(inp["value"]), inp["spatial_shapes"].cpu().numpy(), inp["level_start_index"].cpu().numpy(),
+            f64(inp["sampling_locations"]), f64(inp["attention_weights"]))
+    out = msda_oracle.forward(*args)
+    gv, gl, ga = msda_oracle.backward(f64(inp["grad_output"]), *args)
+    return out, gv, gl, ga
+
+
+@pytest.mark.parametrize("kind,dtype,tol", [("enc", torch.float32, 1e-4), ("dec", torch.float32, 1e-4),
+                                            ("enc", torch.bfloat16, 1e-2), ("dec", torch.bfloat16, 1e-2)])
+def test_cfg1_vs_oracle(kind, dtype, tol):
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, kind, DEV, dtype=dtype, seed=5, wild_fraction=0.1)
+    out_t, gv_t, gl_t, ga_t = _oracle_truth(inp)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    out = MSDA.ms_deform_attn_forward(*a, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    assert _maxerr(out.float().cpu().numpy(), out_t) < tol
+    assert _maxerr(gv.float().cpu().numpy(), gv_t) < tol
+    assert _maxerr(gl.float().cpu().numpy(), gl_t) < 2 * tol
+    assert _maxerr(ga.float().cpu().numpy(), ga_t) < tol
+
+
+@pytest.mark.parametrize("shape", [
+    dict(shapes=[(7, 9)], N=1, M=1, D=32, Lq=1, P=1),                 # a single tap
+    dict(shapes=[(5, 6), (3, 3)], N=3, M=5, D=32, Lq=13, P=3),        # ragged: odd heads, P=3, pairs % 4 != 0
+    dict(shapes=[(4, 4)] * 8, N=1, M=2, D=32, Lq=7, P=4),             # 8 levels, 32 taps (largest fast-path tap count)
+    dict(shapes=[(4, 4)] * 9, N=1, M=2, D=32, Lq=7, P=4),             # 9 levels -> generic path
+    dict(shapes=[(6, 5), (2, 2)], N=2, M=3, D=16, Lq=10, P=2),        # D=16 (4 lanes per row)
+    dict(shapes=[(6, 5), (2, 2)], N=2, M=3, D=64, Lq=10, P=4),        # D=64 (16 lanes per row)
+    dict(shapes=[(6, 5), (2, 2)], N=2, M=3, D=24, Lq=10, P=4),        # D=24 -> generic path
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ragged_shapes_vs_oracle(shape, dtype):
+    if dtype == torch.bfloat16 and shape["D"] == 16:
+        pytest.skip("bf16 D=16 is routed to the generic kernel; covered by D=24")
+    g = torch.Generator().manual_seed(21)
+    ss = torch.as_tensor(shape["shapes"], dtype=torch.long)
+    L = ss.shape[0]
+    lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    S = int(ss.prod(1).sum())
+    N, M, D, Lq, P = (shape[k] for k in ("N", "M", "D", "Lq", "P"))
+    inp = dict(
+        value=torch.randn(N, S, M, D, generator=g).to(DEV, dtype), spatial_shapes=ss.to(DEV),
+        level_start_index=lsi.to(DEV),
+        sampling_locations=(torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3).to(DEV),
+        attention_weights=torch.rand(N, Lq, M, L, P, generator=g).to(DEV),
+        grad_output=torch.randn(N, Lq, M * D, generator=g).to(DEV, dtype))
+    out_t, gv_t, gl_t, ga_t = _oracle_truth(inp)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    out = MSDA.ms_deform_attn_forward(*a, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    assert _maxerr(out.float().cpu().numpy(), out_t) < tol
+    assert _maxerr(gv.float().cpu().numpy(), gv_t) < tol
+    assert _maxerr(gl.float().cpu().numpy(), gl_t) < 2 * tol
+    assert _maxerr(ga.float().cpu().numpy(), ga_t) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (3) BASELINE.json full sizes: identities that do not need the oracle at full size, plus an oracle spot check
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfgname,kind", [("cfg2", "enc"), ("cfg2", "dec"), ("cfg3", "enc"), ("cfg4", "enc")])
+def test_full_size_identities_fp32(cfgname, kind):
+    cfg = CONFIGS[cfgname]
+    inp = make_inputs(cfg, kind, DEV, seed=9, wild_fraction=0.05)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    out = MSDA.ms_deform_attn_forward(*a, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    torch.cuda.synchronize()
+    g = inp["grad_output"].double()
+    inner = (out.double() * g).sum().item()
+    # out is linear in value and in attention_weights (Euler): <out, g> = <value, grad_value> = <attn, grad_attn>
+    iv = (inp["value"].double() * gv.double()).sum().item()
+    ia = (inp["attention_weights"].double() * ga.double()).sum().item()
+    ref = (out.double().abs() * g.abs()).sum().item()
+    assert abs(inner - iv) < 1e-5 * ref and abs(inner - ia) < 1e-5 * ref
+    # linearity: f(2 v) = 2 f(v) exactly in fp32 (power-of-two scaling commutes with every rounding)
+    out2 = MSDA.ms_deform_attn_forward(inp["value"] * 2, *a[1:], 64)
+    assert torch.equal(out2, out * 2)
+    # forward is deterministic
+    assert torch.equal(MSDA.ms_deform_attn_forward(*a, 64), out)
+    # oracle spot check on a strided subset of queries (forward, grad_loc, grad_attn are per-query)
+    Lq = a[3].shape[1]
+    idx = torch.arange(0, Lq, max(1, Lq // 257), device=DEV)
+    sub = dict(inp)
+    sub["sampling_locations"] = a[3][:, idx].contiguous()
+    sub["attention_weights"] = a[4][:, idx].contiguous()
+    sub["grad_output"] = inp["grad_output"][:, idx].contiguous()
+    out_t, _, gl_t, ga_t = _oracle_truth(sub)
+    assert _maxerr(out[:, idx].cpu().numpy(), out_t) < 1e-4
+    assert _maxerr(gl[:, idx].cpu().numpy(), gl_t) < 2e-4
+    assert _maxerr(ga[:, idx].cpu().numpy(), ga_t) < 1e-4
+
+
+def test_full_size_grad_value_vs_oracle_fp32():
+    """cfg2 encoder call, whole grad_value against the fp32 C oracle run on all host cores."""
+    cfg = CONFIGS["cfg2"]
+    inp = make_inputs(cfg, "enc", DEV, seed=10)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    n = lambda t: t.cpu().numpy()
+    gv_t, gl_t, ga_t = msda_oracle.backward(n(inp["grad_output"]), n(a[0]), n(a[1]), n(a[2]), n(a[3]), n(a[4]))
+    assert _maxerr(n(gv), gv_t.astype(np.float64)) < 1e-4
+    assert _maxerr(n(gl), gl_t.astype(np.float64)) < 2e-4
+    assert _maxerr(n(ga), ga_t.astype(np.float64)) < 1e-4
+
+
+def test_full_size_bf16_cfg3():
+    cfg = CONFIGS["cfg3"]
+    inp = make_inputs(cfg, "enc", DEV, dtype=torch.bfloat16, seed=11)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    out = MSDA.ms_deform_attn_forward(*a, 64)
+    ref = MSDA.ms_deform_attn_forward(inp["value"].float(), *a[1:], 64)       # fp32 kernel on the same bf16 values
+    assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    gv32, gl32, ga32 = MSDA.ms_deform_attn_backward(inp["value"].float(), *a[1:], inp["grad_output"].float(), 64)
+    assert (gv.float() - gv32).abs().max().item() < 1e-2 * gv32.abs().max().item()
+    assert (gl - gl32).abs().max().item() < 1e-3 * gl32.abs().max().item()
+    assert (ga - ga32).abs().max().item() < 1e-3 * ga32.abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (4) the reference's own test (ops/test.py) as asserts
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_test_inputs(channels, dtype):
+    N, M, Lq, L, P = 1, 2, 2, 2, 2                                  # ops/test.py:21-22
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=DEV)                     # :23
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))                      # :24
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)                                            # :28
+    value = (torch.rand(N, S, M, channels, device=DEV) * 0.01).to(dtype)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=DEV).to(dtype)
+    attn = torch.rand(N, Lq, M, L, P, device=DEV) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).to(dtype)
+    return value, shapes, lsi, loc, attn
+
+
+def test_reference_check_forward_double_and_float():
+    for dtype, kw in ((torch.float64, {}), (torch.float32, dict(rtol=1e-2, atol=1e-3))):          # :40, :56
+        value, shapes, lsi, loc, attn = _ref_test_inputs(2, dtype)
+        want = msda_oracle.core_pytorch_port(value.cpu(), shapes.cpu(), loc.cpu(), attn.cpu())
+        got = MSDeformAttnFunction.apply(value, shapes, lsi, loc, attn, 2).cpu()
+        assert torch.allclose(got, want, **kw)
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])                        # ops/test.py:85
+def test_reference_gradcheck_fp64(channels):
+    value, shapes, lsi, loc, attn = _ref_test_inputs(channels, torch.float64)
+    value.requires_grad_(True); loc.requires_grad_(True); attn.requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autograd wrappers, error behaviour, streams
+# ---------------------------------------------------------------------------------------------------------------
+def test_autograd_function_fp32_and_bf16():
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "dec", DEV, seed=3)
+    out_t, gv_t, gl_t, ga_t = _oracle_truth(inp)
+    for fn, tol in ((MSDeformAttnFunction, 1e-4), (MSDeformAttnFunctionBF16, 1e-2)):
+        v = inp["value"].clone().requires_grad_(True)
+        lo = inp["sampling_locations"].clone().requires_grad_(True)
+        at = inp["attention_weights"].clone().requires_grad_(True)
+        out = fn.apply(v, inp["spatial_shapes"], inp["level_start_index"], lo, at, 64)
+        out.backward(inp["grad_output"].to(out.dtype))
+        assert _maxerr(out.float().detach().cpu().numpy(), out_t) < tol
+        assert _maxerr(v.grad.float().cpu().numpy(), gv_t) < tol
+        assert _maxerr(lo.grad.cpu().numpy(), gl_t) < 2 * tol
+        assert _maxerr(at.grad.cpu().numpy(), ga_t) < tol
+
+
+def test_autocast_casts_to_fp32_like_reference():
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "dec", DEV, seed=4)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = MSDeformAttnFunction.apply(inp["value"].bfloat16(), inp["spatial_shapes"], inp["level_start_index"],
+                                         inp["sampling_locations"], inp["attention_weights"], 64)
+    assert out.dtype == torch.float32                  # custom_fwd(cast_inputs=float32), func.py:23
+
+
+def test_errors_match_reference_convention():
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "dec", DEV, seed=4)
+    a = [inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"]]
+    with pytest.raises(RuntimeError, match="contiguous"):
+        MSDA.ms_deform_attn_forward(a[0].transpose(2, 3).contiguous().transpose(2, 3), *a[1:], 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_forward(a[0].cpu(), *a[1:], 64)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        MSDA.ms_deform_attn_forward(a[0], a[1].cpu(), *a[2:], 64)
+    v3 = torch.cat([a[0]] * 3)
+    lo3, at3 = torch.cat([a[3]] * 3), torch.cat([a[4]] * 3)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        MSDA.ms_deform_attn_forward(v3, a[1], a[2], lo3, at3, 2)          # 3 % 2 != 0, cu:52
+    assert MSDA.ms_deform_attn_forward(v3, a[1], a[2], lo3, at3, 64).shape[0] == 3
+
+
+def test_runs_on_the_callers_stream():
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "enc", DEV, seed=6)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    want = MSDA.ms_deform_attn_forward(*a, 64)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = MSDA.ms_deform_attn_forward(*a, 64)
+    s.synchronize()
+    assert torch.equal(got, want)
+
+
+def test_launch_counter_counts_our_kernels():
+    lib = _cabi.load()
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "dec", DEV, seed=6)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    before = lib.msda_launch_count()
+    MSDA.ms_deform_attn_forward(*a, 64)
+    MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    assert lib.msda_launch_count() - before == 2

@@ -1,0 +1,270 @@
+// msda_cabi.cu -- the C ABI declared in include/msda_b200.h: argument checks, kernel routing, launches.
+// Replaces the reference host wrappers ms_deform_attn_cuda_forward/backward (ops/src/cuda/ms_deform_attn_cuda.cu)
+// and launchers ms_deformable_im2col_cuda / ms_deformable_col2im_cuda (ms_deform_im2col_cuda.cuh:923-954,956-1327).
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/msda_b200.h"
+#include "msda_generic.cuh"
+#include "msda_tiled.cuh"
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+struct Dims { int N, S, M, D, L, Lq, P; };
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_dims(const Dims &d) {
+    if (d.N <= 0 || d.S <= 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.Lq <= 0 || d.P <= 0) return MSDA_E_BADARG;
+    // rows are indexed with int32 inside a batch element; tap counts with int64 everywhere.
+    if ((long long)d.S >= (1ll << 30)) return MSDA_E_TOOLARGE;
+    if ((long long)d.N * d.Lq * d.M >= (1ll << 40)) return MSDA_E_TOOLARGE;
+    return 0;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ---- routing ------------------------------------------------------------------------------------------------
+// Fast path: D in {16,32,64} (fp32) / {32,64} (bf16), L <= kMaxLevels, L*P <= 32.  LP_MAX is the compile-time tap
+// capacity (taps beyond L*P are dead: zero weight, row 0).
+bool fast_ok(int dtype_bytes, int D, int L, int P) {
+    if (L > msda::kMaxLevels || L * P > 32) return false;
+    if (dtype_bytes == 4) return D == 16 || D == 32 || D == 64;
+    if (dtype_bytes == 2) return D == 32 || D == 64;
+    return false;
+}
+
+// Work decomposition for the tiled kernels: contiguous chunks of (b,q,m) pairs per CTA so that neighbouring queries
+// (which sample neighbouring rows) share an SM's L1; a few chunks per resident CTA slot for balance.
+struct Chunking { int grid; int pairs_per_cta; };
+Chunking chunk(long long npairs, int pairs_per_iter /* nwarps * GPW */) {
+    const long long iters = (npairs + pairs_per_iter - 1) / pairs_per_iter;
+    const long long target_ctas = (long long)num_sms() * 16;
+    long long iters_per_cta = (iters + target_ctas - 1) / target_ctas;
+    if (iters_per_cta < 1) iters_per_cta = 1;
+    Chunking c;
+    c.pairs_per_cta = (int)(iters_per_cta * pairs_per_iter);
+    c.grid = (int)((npairs + c.pairs_per_cta - 1) / c.pairs_per_cta);
+    return c;
+}
+
+template <typename T, int D, int LP_MAX>
+cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                       const Dims &d, T *out, cudaStream_t st) {
+    constexpr int GPW = 32 / (D / msda::RowVec<T>::kElems);
+    const long long npairs = (long long)d.N * d.Lq * d.M;
+    const Chunking c = chunk(npairs, (msda::kTiledThreads / 32) * GPW);
+    msda::msda_fwd_tiled<T, D, LP_MAX><<<c.grid, msda::kTiledThreads, 0, st>>>(
+        value, shapes, lsi, loc, attn, d.S, d.M, d.L, d.Lq, d.P, npairs, c.pairs_per_cta, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T, int D, int LP_MAX>
+cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+                       const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
+    constexpr int GPW = 32 / (D / msda::RowVec<T>::kElems);
+    const long long npairs = (long long)d.N * d.Lq * d.M;
+    const Chunking c = chunk(npairs, (msda::kTiledThreads / 32) * GPW);
+    msda::msda_bwd_tiled<T, D, LP_MAX><<<c.grid, msda::kTiledThreads, 0, st>>>(
+        grad_out, value, shapes, lsi, loc, attn, d.S, d.M, d.L, d.Lq, d.P, npairs, c.pairs_per_cta, gv, gl, ga);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+#define MSDA_ROUTE_LP(T, DD, CALL)                                   \
+    (LP <= 16 ? CALL<T, DD, 16> : CALL<T, DD, 32>)
+
+template <typename T>
+cudaError_t fwd_fast(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                     const Dims &d, T *out, cudaStream_t st) {
+    const int LP = d.L * d.P;
+    switch (d.D) {
+        case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st); break;
+        case 32: return MSDA_ROUTE_LP(T, 32, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st);
+        case 64: return MSDA_ROUTE_LP(T, 64, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename T>
+cudaError_t bwd_fast(const T *go, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+                     const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
+    const int LP = d.L * d.P;
+    switch (d.D) {
+        case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st); break;
+        case 32: return MSDA_ROUTE_LP(T, 32, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
+        case 64: return MSDA_ROUTE_LP(T, 64, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename T, typename TL>
+cudaError_t fwd_generic(const T *value, const int64_t *shapes, const int64_t *lsi, const TL *loc, const TL *attn,
+                        const Dims &d, T *out, cudaStream_t st) {
+    const long long total = (long long)d.N * d.Lq * d.M * d.D;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    msda::msda_fwd_generic<T, TL><<<(int)blocks, 256, 0, st>>>(value, shapes, lsi, loc, attn, d.S, d.M, d.D, d.L, d.Lq,
+                                                               d.P, total, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T, typename TL, typename GA>
+cudaError_t bwd_generic(const T *go, const T *value, const int64_t *shapes, const int64_t *lsi, const TL *loc,
+                        const TL *attn, const Dims &d, GA *gv, TL *gl, TL *ga, cudaStream_t st) {
+    const long long npairs = (long long)d.N * d.Lq * d.M;
+    int threads = ((d.D + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    long long blocks = npairs;
+    const long long cap = (long long)num_sms() * 64;
+    if (blocks > cap) blocks = cap;
+    msda::msda_bwd_generic<T, TL, GA><<<(int)blocks, threads, 0, st>>>(go, value, shapes, lsi, loc, attn, d.S, d.M, d.D,
+                                                                       d.L, d.Lq, d.P, npairs, gv, gl, ga);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char *msda_strerror(int code) {
+    if (code == 0) return "success";
+    if (code == MSDA_E_BADARG) return "msda: bad argument (null/misaligned pointer or non-positive dimension)";
+    if (code == MSDA_E_TOOLARGE) return "msda: problem too large for the kernel index types";
+    if (code == MSDA_E_NODEVICE) return "msda: no CUDA device";
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "msda: unknown error";
+}
+
+int msda_uses_fast_path(int dtype_bytes, int D, int L, int P) { return fast_ok(dtype_bytes, D, L, P) ? 1 : 0; }
+
+uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+#define MSDA_CHECK_PTRS(...)                                             \
+    do {                                                                 \
+        const void *ptrs_[] = {__VA_ARGS__};                             \
+        for (const void *p_ : ptrs_)                                     \
+            if (p_ == nullptr || !aligned16(p_)) return MSDA_E_BADARG;   \
+    } while (0)
+
+int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const float *sampling_loc, const float *attn_weight, int N, int S, int M, int D, int L, int Lq,
+                     int P, float *out, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    MSDA_CHECK_PTRS(value, sampling_loc, attn_weight, out);
+    if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fast_ok(4, D, L, P)) return (int)fwd_fast<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
+    return (int)fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
+}
+
+int msda_forward_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const double *sampling_loc, const double *attn_weight, int N, int S, int M, int D, int L, int Lq,
+                     int P, double *out, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !out) return MSDA_E_BADARG;
+    return (int)fwd_generic<double, double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out,
+                                            static_cast<cudaStream_t>(stream));
+}
+
+int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *sampling_loc, const float *attn_weight, int N, int S, int M, int D, int L, int Lq,
+                      int P, uint16_t *out, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    MSDA_CHECK_PTRS(value, sampling_loc, attn_weight, out);
+    if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
+    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
+    if (fast_ok(2, D, L, P)) return (int)fwd_fast<__nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
+    return (int)fwd_generic<__nv_bfloat16, float>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
+}
+
+int msda_backward_f32(const float *grad_out, const float *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const float *sampling_loc, const float *attn_weight, int N,
+                      int S, int M, int D, int L, int Lq, int P, float *grad_value, float *grad_sampling_loc,
+                      float *grad_attn_weight, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    MSDA_CHECK_PTRS(grad_out, value, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight);
+    if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * S * M * D, st);
+    if (err != cudaSuccess) return (int)err;
+    if (fast_ok(4, D, L, P))
+        return (int)bwd_fast<float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
+                                    grad_value, grad_sampling_loc, grad_attn_weight, st);
+    return (int)bwd_generic<float, float, float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, d, grad_value, grad_sampling_loc, grad_attn_weight, st);
+}
+
+int msda_backward_f64(const double *grad_out, const double *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const double *sampling_loc, const double *attn_weight, int N,
+                      int S, int M, int D, int L, int Lq, int P, double *grad_value, double *grad_sampling_loc,
+                      double *grad_attn_weight, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    if (!grad_out || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_value ||
+        !grad_sampling_loc || !grad_attn_weight)
+        return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(double) * (size_t)N * S * M * D, st);
+    if (err != cudaSuccess) return (int)err;
+    return (int)bwd_generic<double, double, double>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
+                                                    attn_weight, d, grad_value, grad_sampling_loc, grad_attn_weight, st);
+}
+
+int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const float *sampling_loc, const float *attn_weight, int N,
+                       int S, int M, int D, int L, int Lq, int P, float *grad_value_f32, uint16_t *grad_value,
+                       float *grad_sampling_loc, float *grad_attn_weight, void *stream) {
+    const Dims d{N, S, M, D, L, Lq, P};
+    if (int e = check_dims(d)) return e;
+    MSDA_CHECK_PTRS(grad_out, value, sampling_loc, attn_weight, grad_value_f32, grad_sampling_loc, grad_attn_weight);
+    if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nval = (size_t)N * S * M * D;
+    cudaError_t err = cudaMemsetAsync(grad_value_f32, 0, sizeof(float) * nval, st);
+    if (err != cudaSuccess) return (int)err;
+    const __nv_bfloat16 *go = reinterpret_cast<const __nv_bfloat16 *>(grad_out);
+    const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
+    if (fast_ok(2, D, L, P))
+        err = bwd_fast<__nv_bfloat16>(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
+                                      grad_value_f32, grad_sampling_loc, grad_attn_weight, st);
+    else
+        err = bwd_generic<__nv_bfloat16, float, float>(go, v, spatial_shapes, level_start_index, sampling_loc,
+                                                       attn_weight, d, grad_value_f32, grad_sampling_loc,
+                                                       grad_attn_weight, st);
+    if (err != cudaSuccess) return (int)err;
+    if (grad_value != nullptr) {
+        long long blocks = (long long)((nval + 255) / 256);
+        const long long cap = (long long)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        msda::msda_f32_to_bf16<<<(int)blocks, 256, 0, st>>>(grad_value_f32, reinterpret_cast<__nv_bfloat16 *>(grad_value),
+                                                            (long long)nval);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        err = cudaGetLastError();
+    }
+    return (int)err;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// msda_common.cuh -- shared device helpers for the sm_100a multi-scale deformable attention kernels.
+//
+// Semantics follow the reference kernels in
+//   /root/reference/projects/UNINEXT/uninext/models/deformable_detr/ops/src/cuda/ms_deform_im2col_cuda.cuh ("cuh"):
+//   pixel mapping cuh:285-286, validity window cuh:288, per-corner predicates cuh:56-78, weights cuh:80-83,
+//   gradients cuh:112-158.  Nothing here is derived from that file's code structure: a tap is resolved ONCE by one
+//   lane into (clamped row indices, masked corner weights) and shared with the lanes that own the channels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr int kMaxLevels = 8;         // level table kept in shared memory by the tiled kernels
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// Geometry of one bilinear tap, resolved against one level map.
+//   r0 / r1 : row index (within one batch element, i.e. in [0, S)) of the clamped (h0, w0) / (h1, w0) corners.
+//             Clamping keeps every address legal; corners outside the map get weight 0 through `mask`.
+//   dw      : 1 when the clamped w1 differs from the clamped w0 (i.e. the right-hand corners are one row further).
+//   mask    : bit k set <=> corner k (00, 01, 10, 11) lies inside the map AND the tap passes the window test.
+struct TapGeom {
+    float lh, lw;
+    int r0, r1;
+    int dw;
+    unsigned mask;
+};
+
+__device__ __forceinline__ TapGeom tap_geometry(float x, float y, int H, int W, int start) {
+    TapGeom g;
+    // Same rounding sequence as the reference: product rounded to fp32, then the 0.5 shift (cuh:285-286).
+    const float h_im = __fadd_rn(__fmul_rn(y, (float)H), -0.5f);
+    const float w_im = __fadd_rn(__fmul_rn(x, (float)W), -0.5f);
+    const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);   // cuh:288
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    g.lh = h_im - hf;
+    g.lw = w_im - wf;
+    int h0 = inside ? (int)hf : 0;
+    int w0 = inside ? (int)wf : 0;
+    const int h1 = h0 + 1, w1 = w0 + 1;
+    unsigned m = 0;
+    if (inside) {
+        const bool t = h0 >= 0, b = h1 <= H - 1, l = w0 >= 0, r = w1 <= W - 1;     // cuh:56,62,68,74
+        m = (unsigned)(t && l) | ((unsigned)(t && r) << 1) | ((unsigned)(b && l) << 2) | ((unsigned)(b && r) << 3);
+    }
+    g.mask = m;
+    const int ch0 = max(h0, 0), ch1 = min(h1, H - 1), cw0 = max(w0, 0), cw1 = min(w1, W - 1);
+    g.r0 = start + ch0 * W + cw0;
+    g.r1 = start + ch1 * W + cw0;
+    g.dw = cw1 - cw0;
+    return g;
+}
+
+// 16-byte vector access to one slice of a value / grad row, widened to fp32 registers.
+template <typename T> struct RowVec;
+
+template <> struct RowVec<float> {
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ void load(const float *p, float (&v)[4]) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static __forceinline__ void store(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+template <> struct RowVec<__nv_bfloat16> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        const unsigned u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                     // bf16 -> fp32 is a 16-bit left shift
+            v[2 * i] = __uint_as_float(u[i] << 16);
+            v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[8]) {
+        unsigned u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            u[i] = *reinterpret_cast<const unsigned *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+};
+
+// Vector reduction into global memory: one 16-byte red per call (sm_90+), no return value.
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+}  // namespace msda
