@@ -38,6 +38,21 @@ def _maxerr(got, want):
     return float(np.abs(got.astype(np.float64) - want).max()) / _scale(want)
 
 
+def _outlier_frac(got, want, tol):
+    """Fraction of entries off by more than tol*scale.  grad_sampling_locations is piecewise constant in the location:
+    a tap whose fp32 pixel coordinate rounds into the neighbouring cell (probability ~1e-5 per tap) legitimately differs
+    by O(1) from an fp64 evaluation, exactly as the reference's fp32 kernel does."""
+    err = np.abs(got.astype(np.float64) - want) / _scale(want)
+    return float((err > tol).mean())
+
+
+def _gl_ok(got, want, tol):
+    """grad_sampling_locations check against fp64 truth: every entry within tol, except a <=1e-4 fraction (and at most
+    a handful) of cell-boundary taps (see _outlier_frac)."""
+    bad = _outlier_frac(got, want, tol) * want.size
+    return bad <= max(2.0, 1e-4 * want.size)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (1) golden vectors from the reference
 # ---------------------------------------------------------------------------------------------------------------
@@ -113,7 +128,7 @@ def test_cfg1_vs_oracle(kind, dtype, tol):
     gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
     assert _maxerr(out.float().cpu().numpy(), out_t) < tol
     assert _maxerr(gv.float().cpu().numpy(), gv_t) < tol
-    assert _maxerr(gl.float().cpu().numpy(), gl_t) < 2 * tol
+    assert _gl_ok(gl.float().cpu().numpy(), gl_t, 2 * tol)
     assert _maxerr(ga.float().cpu().numpy(), ga_t) < tol
 
 
@@ -150,7 +165,7 @@ def test_ragged_shapes_vs_oracle(shape, dtype):
     gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
     assert _maxerr(out.float().cpu().numpy(), out_t) < tol
     assert _maxerr(gv.float().cpu().numpy(), gv_t) < tol
-    assert _maxerr(gl.float().cpu().numpy(), gl_t) < 2 * tol
+    assert _gl_ok(gl.float().cpu().numpy(), gl_t, 2 * tol)
     assert _maxerr(ga.float().cpu().numpy(), ga_t) < tol
 
 
@@ -187,8 +202,14 @@ def test_full_size_identities_fp32(cfgname, kind):
     sub["grad_output"] = inp["grad_output"][:, idx].contiguous()
     out_t, _, gl_t, ga_t = _oracle_truth(sub)
     assert _maxerr(out[:, idx].cpu().numpy(), out_t) < 1e-4
-    assert _maxerr(gl[:, idx].cpu().numpy(), gl_t) < 2e-4
+    assert _outlier_frac(gl[:, idx].cpu().numpy(), gl_t, 2e-4) < 1e-4
     assert _maxerr(ga[:, idx].cpu().numpy(), ga_t) < 1e-4
+    # strict check against the fp32 oracle, which takes the same rounding sequence for the pixel coordinate
+    n = lambda t: t.cpu().numpy()
+    _, gl32, ga32 = msda_oracle.backward(n(sub["grad_output"]), n(a[0]), n(a[1]), n(a[2]), n(sub["sampling_locations"]),
+                                         n(sub["attention_weights"]))
+    assert _maxerr(n(gl[:, idx]), gl32.astype(np.float64)) < 2e-4
+    assert _maxerr(n(ga[:, idx]), ga32.astype(np.float64)) < 1e-4
 
 
 def test_full_size_grad_value_vs_oracle_fp32():
@@ -252,6 +273,30 @@ def test_reference_gradcheck_fp64(channels):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# (5) against the reference's own CUDA kernels (oracle/_ref, built from /root/reference by oracle/build_refcuda.sh)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfgname,kind,dtype", [("cfg1", "enc", torch.float32), ("cfg2", "enc", torch.float32),
+                                                ("cfg2", "dec", torch.float32), ("cfg1", "dec", torch.float64)])
+def test_against_reference_cuda_kernels(cfgname, kind, dtype):
+    from oracle import refcuda
+    if not refcuda.available():
+        pytest.skip("oracle/_ref/libmsda_refcuda.so not built (needs /root/reference at build time)")
+    inp = make_inputs(CONFIGS[cfgname], kind, DEV, dtype=dtype, seed=13, wild_fraction=0.05)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
+         inp["attention_weights"])
+    ref_out = refcuda.forward(*a)
+    ref_gv, ref_gl, ref_ga = refcuda.backward(*a, inp["grad_output"])
+    out = MSDA.ms_deform_attn_forward(*a, 64)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
+    tol = 1e-4 if dtype == torch.float32 else 1e-11
+    rel = lambda x, y: ((x - y).abs().max() / y.abs().max().clamp_min(1e-30)).item()
+    assert rel(out, ref_out) < tol
+    assert rel(gv, ref_gv) < tol
+    assert rel(gl, ref_gl) < 2 * tol
+    assert rel(ga, ref_ga) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # autograd wrappers, error behaviour, streams
 # ---------------------------------------------------------------------------------------------------------------
 def test_autograd_function_fp32_and_bf16():
@@ -266,7 +311,7 @@ def test_autograd_function_fp32_and_bf16():
         out.backward(inp["grad_output"].to(out.dtype))
         assert _maxerr(out.float().detach().cpu().numpy(), out_t) < tol
         assert _maxerr(v.grad.float().cpu().numpy(), gv_t) < tol
-        assert _maxerr(lo.grad.cpu().numpy(), gl_t) < 2 * tol
+        assert _gl_ok(lo.grad.cpu().numpy(), gl_t, 2 * tol)
         assert _maxerr(at.grad.cpu().numpy(), ga_t) < tol
 
 

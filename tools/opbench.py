@@ -21,6 +21,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--jitter", type=float, default=2.0)
 ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--ref", action="store_true", help="time the reference's own CUDA kernels (oracle/_ref) instead")
 a = ap.parse_args()
 
 cfg = CONFIGS[a.config]
@@ -28,6 +29,20 @@ dt = torch.float32 if a.dtype == "fp32" else torch.bfloat16
 inp = make_inputs(cfg, a.kind, "cuda", dtype=dt, seed=0, jitter_px=a.jitter)
 args = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+if a.ref:
+    from oracle import refcuda
+    assert refcuda.available() and a.dtype == "fp32"
+    ref_out = torch.empty_like(inp["grad_output"])
+    ref_g = (torch.empty_like(args[0]), torch.empty_like(args[3]), torch.empty_like(args[4]))
+
+    class MSDA:  # noqa: F811  (same call shape; at::zeros / zeros_like of the reference wrapper are included)
+        @staticmethod
+        def ms_deform_attn_forward(v, ss, lsi, loc, attn, step):
+            return refcuda.forward(v, ss, lsi, loc, attn)
+
+        @staticmethod
+        def ms_deform_attn_backward(v, ss, lsi, loc, attn, go, step):
+            return refcuda.backward(v, ss, lsi, loc, attn, go, outs=ref_g)
 fw, bw = [], []
 for i in range(a.warmup + a.iters):
     if not a.no_flush:
@@ -45,7 +60,7 @@ fw.sort(); bw.sort()
 mf, mb = fw[len(fw) // 2], bw[len(bw) // 2]
 smp = cfg.samples(a.kind)
 el = 4 if a.dtype == "fp32" else 2
-print(json.dumps({"config": cfg.name, "kind": a.kind, "dtype": a.dtype, "samples": smp,
+print(json.dumps({"impl": "reference-cuda" if a.ref else "b200", "config": cfg.name, "kind": a.kind, "dtype": a.dtype, "samples": smp,
                   "fwd_ms": round(mf, 4), "bwd_ms": round(mb, 4),
                   "fwd_gsamples": round(smp / mf / 1e6, 2), "bwd_gsamples": round(smp / mb / 1e6, 2),
                   "fwd_alg_GBps": round(algorithmic_bytes(cfg, a.kind, el, "fwd") / mf / 1e6, 1),
