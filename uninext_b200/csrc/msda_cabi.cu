@@ -3,6 +3,7 @@
 // and launchers ms_deformable_im2col_cuda / ms_deformable_col2im_cuda (ms_deform_im2col_cuda.cuh:923-954,956-1327).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/msda_b200.h"
 #include "msda_generic.cuh"
@@ -44,28 +45,66 @@ bool fast_ok(int dtype_bytes, int D, int L, int P) {
     return false;
 }
 
-// Work decomposition for the tiled kernels: contiguous chunks of (b,q,m) pairs per CTA so that neighbouring queries
-// (which sample neighbouring rows) share an SM's L1; a few chunks per resident CTA slot for balance.
-struct Chunking { int grid; int pairs_per_cta; };
-Chunking chunk(long long npairs, int pairs_per_iter /* nwarps * GPW */) {
-    const long long iters = (npairs + pairs_per_iter - 1) / pairs_per_iter;
-    const long long target_ctas = (long long)num_sms() * 16;
-    long long iters_per_cta = (iters + target_ctas - 1) / target_ctas;
-    if (iters_per_cta < 1) iters_per_cta = 1;
-    Chunking c;
-    c.pairs_per_cta = (int)(iters_per_cta * pairs_per_iter);
-    c.grid = (int)((npairs + c.pairs_per_cta - 1) / c.pairs_per_cta);
-    return c;
+bool use_fast(int dtype_bytes, const Dims &d) {      // the tiled kernels index (b,q,m) pairs with 31 bits
+    return fast_ok(dtype_bytes, d.D, d.L, d.P) && (long long)d.N * d.Lq * d.M < (1ll << 31);
+}
+
+// Persistent launch: one CTA per resident slot (SM count x occupancy); tiles are walked with a grid stride inside the
+// kernel, which derives the tile map from the device-resident level table (no host read of spatial_shapes).
+template <typename K>
+int resident_ctas(K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, msda::kTiledThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * num_sms();
+}
+
+// Slot order.  Measured on B200 (profiles/r01c_*_ncu.md, gpurun_out r01d sweep): the 8x8-pixel patch order lifts the
+// forward L1 sector hit rate from 39% to 75% and cuts L2 traffic 2.4x, but the kernels are bound by the LSU's
+// global-load issue rate (~7.5 cycles per 512-byte LDG.128 per SM), not by L1 misses, so run time does not move while
+// partially filled border patches cost 7-15% idle slots.  Linear order is therefore the default; MSDA_PATCHES=1
+// re-enables the patch order for experiments.
+int allow_patches() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MSDA_PATCHES"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+
+constexpr int kFwdMinCtas = 4, kBwdMinCtas = 2;     // r01d sweep: fwd flat for 3..5, bwd best at 2 (128 regs, no spills)
+
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
 }
 
 template <typename T, int D, int LP_MAX>
 cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                        const Dims &d, T *out, cudaStream_t st) {
-    constexpr int GPW = 32 / (D / msda::RowVec<T>::kElems);
-    const long long npairs = (long long)d.N * d.Lq * d.M;
-    const Chunking c = chunk(npairs, (msda::kTiledThreads / 32) * GPW);
-    msda::msda_fwd_tiled<T, D, LP_MAX><<<c.grid, msda::kTiledThreads, 0, st>>>(
-        value, shapes, lsi, loc, attn, d.S, d.M, d.L, d.Lq, d.P, npairs, c.pairs_per_cta, out);
+    auto kern = msda::msda_fwd_tiled<T, D, LP_MAX, kFwdMinCtas>;
+    static int slots = resident_ctas(kern);
+#ifdef MSDA_EXPERIMENTS
+    if constexpr (D == 32 && LP_MAX == 16) {
+        static const int want = env_int("MSDA_FWD_CTAS", kFwdMinCtas);
+        static bool once = false;
+        if (!once) {
+            once = true;
+            if (want == 1) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 1>; }
+            if (want == 2) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 2>; }
+            if (want == 3) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 3>; }
+            if (want == 5) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 5>; }
+            if (want == 6) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 6>; }
+            slots = resident_ctas(kern);
+            static auto chosen = kern; (void)chosen;
+        }
+        static auto kept = kern;
+        kern = kept;
+    }
+#endif
+    const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
+    const unsigned tiles_ub = (npairs + msda::kTileSlots - 1) / msda::kTileSlots;      // linear order; patches >= this
+    const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
+    kern<<<grid, msda::kTiledThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P, npairs,
+                                               allow_patches(), out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -73,11 +112,28 @@ cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi
 template <typename T, int D, int LP_MAX>
 cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                        const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
-    constexpr int GPW = 32 / (D / msda::RowVec<T>::kElems);
-    const long long npairs = (long long)d.N * d.Lq * d.M;
-    const Chunking c = chunk(npairs, (msda::kTiledThreads / 32) * GPW);
-    msda::msda_bwd_tiled<T, D, LP_MAX><<<c.grid, msda::kTiledThreads, 0, st>>>(
-        grad_out, value, shapes, lsi, loc, attn, d.S, d.M, d.L, d.Lq, d.P, npairs, c.pairs_per_cta, gv, gl, ga);
+    auto kern = msda::msda_bwd_tiled<T, D, LP_MAX, kBwdMinCtas>;
+    static int slots = resident_ctas(kern);
+#ifdef MSDA_EXPERIMENTS
+    if constexpr (D == 32 && LP_MAX == 16) {
+        static const int want = env_int("MSDA_BWD_CTAS", kBwdMinCtas);
+        static bool once = false;
+        if (!once) {
+            once = true;
+            if (want == 1) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 1>; }
+            if (want == 2) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 2>; }
+            if (want == 4) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 4>; }
+            slots = resident_ctas(kern);
+        }
+        static auto kept = kern;
+        kern = kept;
+    }
+#endif
+    const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
+    const unsigned tiles_ub = (npairs + msda::kTileSlots - 1) / msda::kTileSlots;
+    const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
+    kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
+                                               npairs, allow_patches(), gv, gl, ga);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -171,7 +227,7 @@ int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const in
     MSDA_CHECK_PTRS(value, sampling_loc, attn_weight, out);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (fast_ok(4, D, L, P)) return (int)fwd_fast<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
+    if (use_fast(4, d)) return (int)fwd_fast<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
     return (int)fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
 }
 
@@ -195,7 +251,7 @@ int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
-    if (fast_ok(2, D, L, P)) return (int)fwd_fast<__nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
+    if (use_fast(2, d)) return (int)fwd_fast<__nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
     return (int)fwd_generic<__nv_bfloat16, float>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
 }
 
@@ -210,7 +266,7 @@ int msda_backward_f32(const float *grad_out, const float *value, const int64_t *
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * S * M * D, st);
     if (err != cudaSuccess) return (int)err;
-    if (fast_ok(4, D, L, P))
+    if (use_fast(4, d))
         return (int)bwd_fast<float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                     grad_value, grad_sampling_loc, grad_attn_weight, st);
     return (int)bwd_generic<float, float, float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
@@ -247,7 +303,7 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
     if (err != cudaSuccess) return (int)err;
     const __nv_bfloat16 *go = reinterpret_cast<const __nv_bfloat16 *>(grad_out);
     const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
-    if (fast_ok(2, D, L, P))
+    if (use_fast(2, d))
         err = bwd_fast<__nv_bfloat16>(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                       grad_value_f32, grad_sampling_loc, grad_attn_weight, st);
     else

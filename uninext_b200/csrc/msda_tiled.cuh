@@ -1,16 +1,25 @@
-// msda_tiled.cuh -- the sm_100a fast path: row-vectorised gather kernels (forward and backward).
+// msda_tiled.cuh -- the sm_100a fast path: persistent, row-vectorised gather kernels (forward and backward).
 //
-// Thread mapping (both kernels).  A value row of one head is D contiguous elements; LPR = D / kElems lanes cover it
-// with one 16-byte access each (fp32 D=32: 8 lanes, bf16 D=32: 4 lanes).  A warp therefore carries GPW = 32 / LPR
-// "groups"; each group owns one (batch, query, head) pair at a time.  Work inside a group is split two ways:
+// Thread mapping.  A value row of one head is D contiguous elements; LPR = D / kElems lanes cover it with one 16-byte
+// access each (fp32 D=32: 8 lanes, bf16 D=32: 4 lanes).  A warp therefore carries GPW = 32 / LPR "groups"; each group
+// owns one (batch, query, head) pair at a time.  Work inside a group is split two ways:
 //   stage 1 (by tap):     lane `sub` resolves taps sub, sub+LPR, ... : reads (x, y, a), resolves the bilinear
-//                         geometry once (tap_geometry), keeps it in registers.
-//   stage 2 (by channel): for every tap the owning lane broadcasts 4 masked corner weights + 2 row indices with
-//                         group-wide shuffles; every lane then issues four 16-byte row loads for ITS channel slice.
+//                         geometry once (tap_geometry) and publishes a 24-byte tap record {4 masked corner weights,
+//                         2 clamped row indices} to a per-warp shared-memory slab (conflict-free layout).
+//   stage 2 (by channel): for every tap each lane reads the record (one LDS.128 + one LDS.64, broadcast inside the
+//                         group) and issues four 16-byte row loads for ITS channel slice.
 // This removes the reference forward kernel's 32x-redundant per-channel index arithmetic and scalar loads
 // (cuh:272-296) and the reference backward kernel's per-tap __syncthreads + serial shared-memory reductions
 // (cuh:347-401): the backward channel reduction is a shuffle reduce-scatter that leaves tap j's sums on lane j,
 // i.e. on the lane that already holds that tap's geometry.
+//
+// Work decomposition.  The grid is persistent (SM count x resident CTAs); CTA c walks tiles c, c+G, c+2G, ... of 64
+// (pair) slots.  Two slot orders:
+//   linear  -- slots are consecutive pairs in memory order (decoder-style calls: queries have no spatial structure);
+//   patches -- used when Lq == S and the level table tiles [0, S) exactly, i.e. queries ARE the pixels of the pyramid
+//              (encoder self-attention, deformable_transformer.py:280-292): a tile is one head of an 8x8 pixel patch,
+//              so the rows gathered by neighbouring queries of the same head overlap in L1 while the tile is resident.
+//              Purely a scheduling choice: every pair is still processed exactly once, results do not depend on it.
 #pragma once
 
 #include "msda_common.cuh"
@@ -18,119 +27,205 @@
 namespace msda {
 
 constexpr int kTiledThreads = 256;
+constexpr int kTiledWarps = kTiledThreads / 32;
+constexpr int kPatch = 8;                       // pixel patch edge (patches mode)
+constexpr int kTileSlots = kPatch * kPatch;     // (pair) slots per tile, both modes
 
-template <int LPR>
-__device__ __forceinline__ float group_bcast(float v, int src) { return __shfl_sync(kFullMask, v, src, LPR); }
-template <int LPR>
-__device__ __forceinline__ int group_bcast(int v, int src) { return __shfl_sync(kFullMask, v, src, LPR); }
-
-struct LevelSmem {
+struct WorkMap {
     int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels];
+    int pcols[kMaxLevels];           // patches per patch-row of level l
+    int pfirst[kMaxLevels + 1];      // first patch index of level l within one batch element
+    int patches;                     // 1 when the patch order is in use
+    unsigned ntiles;
 };
 
-__device__ __forceinline__ void load_levels(LevelSmem &lv, const int64_t *shapes, const int64_t *lsi, int L) {
-    if (threadIdx.x < L) {
-        lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
-        lv.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
-        lv.start[threadIdx.x] = (int)lsi[threadIdx.x];
+// Every CTA derives the same map from the (device-resident) level table: no host read of spatial_shapes is needed.
+__device__ __forceinline__ void build_work_map(WorkMap &wm, const int64_t *shapes, const int64_t *lsi, int L, int N,
+                                               int S, int Lq, int M, unsigned npairs, int allow_patches) {
+    if (threadIdx.x == 0) {
+        int run = 0, np = 0;
+        bool tiled = (Lq == S) && allow_patches;
+        for (int l = 0; l < L; ++l) {
+            const int h = (int)shapes[2 * l], w = (int)shapes[2 * l + 1], st = (int)lsi[l];
+            wm.H[l] = h; wm.W[l] = w; wm.start[l] = st;
+            tiled = tiled && (st == run) && h > 0 && w > 0;
+            run += h * w;
+            wm.pcols[l] = (w + kPatch - 1) / kPatch;
+            wm.pfirst[l] = np;
+            np += wm.pcols[l] * ((h + kPatch - 1) / kPatch);
+        }
+        wm.pfirst[L] = np;
+        tiled = tiled && (run == S);
+        wm.patches = tiled ? 1 : 0;
+        wm.ntiles = tiled ? (unsigned)N * (unsigned)M * (unsigned)np : (npairs + kTileSlots - 1) / kTileSlots;
     }
     __syncthreads();
+}
+
+struct TileCtx {          // CTA-uniform description of the current tile
+    int b, m, H, W, start, py0, px0;
+    unsigned base_pair;
+};
+
+__device__ __forceinline__ TileCtx decode_tile(const WorkMap &wm, unsigned tile, int L, int M) {
+    TileCtx t;
+    if (wm.patches) {
+        t.m = (int)(tile % (unsigned)M);               // heads fastest: the 8 tiles of a patch run at about the same
+        unsigned r = tile / (unsigned)M;               // time and share DRAM pages of loc / attn / out
+        const unsigned per_b = (unsigned)wm.pfirst[L];
+        t.b = (int)(r / per_b);
+        int p = (int)(r % per_b);
+        int l = 0;
+        while (l + 1 < L && p >= wm.pfirst[l + 1]) ++l;
+        p -= wm.pfirst[l];
+        t.H = wm.H[l]; t.W = wm.W[l]; t.start = wm.start[l];
+        t.py0 = (p / wm.pcols[l]) * kPatch;
+        t.px0 = (p % wm.pcols[l]) * kPatch;
+        t.base_pair = 0;
+    } else {
+        t.b = t.m = t.H = t.W = t.start = t.py0 = t.px0 = 0;
+        t.base_pair = tile * kTileSlots;
+    }
+    return t;
+}
+
+// Which (b, q, m) pair does this group handle in iteration `it` of the tile?  Returns false for idle slots.
+template <int GPW>
+__device__ __forceinline__ bool slot_pair(const WorkMap &wm, const TileCtx &t, int it, int warp, int grp, int Lq, int M,
+                                          unsigned npairs, unsigned &pair, int &b, int &m) {
+    if (wm.patches) {
+        const int y = t.py0 + warp, x = t.px0 + it * GPW + grp;       // warp = patch row, groups = neighbours in x
+        const bool ok = (y < t.H) && (x < t.W);
+        const int q = ok ? t.start + y * t.W + x : t.start;
+        b = t.b; m = t.m;
+        pair = ((unsigned)t.b * (unsigned)Lq + (unsigned)q) * (unsigned)M + (unsigned)t.m;
+        return ok;
+    }
+    const unsigned p = t.base_pair + (unsigned)(it * kTiledWarps * GPW + warp * GPW + grp);
+    const bool ok = p < npairs;
+    pair = ok ? p : npairs - 1;
+    m = (int)(pair % (unsigned)M);
+    b = (int)((pair / (unsigned)M) / (unsigned)Lq);
+    return ok;
+}
+
+// Per-warp slab for tap records.  Strides are padded so that (a) the LPR records of a group are contiguous (one
+// wavefront per quarter-warp store) and (b) the GPW concurrent broadcast reads fall into disjoint banks.
+template <int LPR>
+struct TapSlab {
+    static constexpr int GPW = 32 / LPR;
+    static constexpr int kStrideW = LPR * 16 + 16;     // bytes between groups, weight records (float4)
+    static constexpr int kStrideR = LPR * 8 + 8;       // bytes between groups, row records (int2)
+    static constexpr int kBytes = GPW * (kStrideW + kStrideR);
+    unsigned char *w, *r;
+    __device__ __forceinline__ TapSlab(unsigned char *warp_base, int grp)
+        : w(warp_base + grp * kStrideW), r(warp_base + GPW * kStrideW + grp * kStrideR) {}
+    __device__ __forceinline__ void put(int j, float4 wt, int2 rows) {
+        *reinterpret_cast<float4 *>(w + j * 16) = wt;
+        *reinterpret_cast<int2 *>(r + j * 8) = rows;
+    }
+    __device__ __forceinline__ float4 weights(int j) const { return *reinterpret_cast<const float4 *>(w + j * 16); }
+    __device__ __forceinline__ int2 rows(int j) const { return *reinterpret_cast<const int2 *>(r + j * 8); }
+};
+
+__device__ __forceinline__ float4 masked_weights(const TapGeom &g, float a) {
+    const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+    return make_float4((g.mask & 1u) ? hh * hw * a : 0.f, (g.mask & 2u) ? hh * g.lw * a : 0.f,
+                       (g.mask & 4u) ? g.lh * hw * a : 0.f, (g.mask & 8u) ? g.lh * g.lw * a : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward:  out[b,q,m,:] = sum_taps a * bilinear(value_l[b,:,m,:], x, y)            (reference cuh:237-299)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int D, int LP_MAX>
-__global__ void __launch_bounds__(kTiledThreads)
+template <typename T, int D, int LP_MAX, int MIN_CTAS>
+__global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
-               int S, int M, int L, int Lq, int P, long long npairs, int pairs_per_cta, T *__restrict__ out)
+               int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches, T *__restrict__ out)
 {
     constexpr int VEC = RowVec<T>::kElems;
     constexpr int LPR = D / VEC;            // lanes per row
     constexpr int GPW = 32 / LPR;           // (b,q,m) pairs in flight per warp
     constexpr int NSL = LP_MAX / LPR;       // taps resolved per lane
+    constexpr int ITERS = kTileSlots / (kTiledWarps * GPW);
     static_assert(D % VEC == 0 && (LPR & (LPR - 1)) == 0 && LPR <= 32 && LP_MAX % LPR == 0, "bad tiling");
+    static_assert(kTileSlots % (kTiledWarps * GPW) == 0 && ITERS >= 1, "tile must be whole iterations");
 
-    __shared__ LevelSmem lv;
-    load_levels(lv, shapes, lsi, L);
+    __shared__ WorkMap wm;
+    __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
     const int LP = L * P;
-    const size_t row_elems = (size_t)M * D;
-    const long long cta_begin = (long long)blockIdx.x * pairs_per_cta;
-    const long long cta_end = min(npairs, cta_begin + (long long)pairs_per_cta);
+    const unsigned row_bytes = (unsigned)(M * D) * (unsigned)sizeof(T);
+    TapSlab<LPR> slab(slab_mem + warp * TapSlab<LPR>::kBytes, grp);
 
-    for (long long p0 = cta_begin + (long long)warp * GPW; p0 < cta_end; p0 += (long long)nwarps * GPW) {
-        const long long pair_raw = p0 + grp;
-        const bool active = pair_raw < cta_end;
-        const long long pair = active ? pair_raw : cta_end - 1;          // keep idle groups on legal addresses
-        const int m = (int)(pair % M);
-        const int b = (int)((pair / M) / Lq);
+    for (unsigned tile = blockIdx.x; tile < wm.ntiles; tile += gridDim.x) {
+        const TileCtx tc = decode_tile(wm, tile, L, M);
+#pragma unroll 1
+        for (int it = 0; it < ITERS; ++it) {
+            unsigned pair; int b, m;
+            const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
 
-        // ---- stage 1: this lane resolves its taps ----
-        float tw[NSL][4];
-        int tr0[NSL], tr1[NSL];
+            // ---- stage 1: this lane resolves its taps (dead taps: zero weight, row 0) ----
+            float4 tw[NSL];
+            int2 tr[NSL];
 #pragma unroll
-        for (int k = 0; k < NSL; ++k) {
-            const int s = sub + k * LPR;
-            tw[k][0] = tw[k][1] = tw[k][2] = tw[k][3] = 0.f;
-            tr0[k] = 0; tr1[k] = 0;
-            if (s < LP && active) {
-                const long long t = pair * LP + s;
-                const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
-                const float a = __ldg(attn + t);
-                const int l = s / P;
-                const TapGeom g = tap_geometry(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l]);
-                const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-                tw[k][0] = (g.mask & 1u) ? hh * hw * a : 0.f;
-                tw[k][1] = (g.mask & 2u) ? hh * g.lw * a : 0.f;
-                tw[k][2] = (g.mask & 4u) ? g.lh * hw * a : 0.f;
-                tw[k][3] = (g.mask & 8u) ? g.lh * g.lw * a : 0.f;
-                tr0[k] = g.r0;
-                tr1[k] = g.r1 | (g.dw << 31);
-            }
-        }
-
-        // ---- stage 2: gather rows for this lane's channel slice ----
-        const T *base = value + (size_t)b * S * row_elems + (size_t)m * D + (size_t)sub * VEC;
-        float acc[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-#pragma unroll
-        for (int k = 0; k < NSL; ++k) {
-#pragma unroll
-            for (int j = 0; j < LPR; ++j) {
-                const float w00 = group_bcast<LPR>(tw[k][0], j);
-                const float w01 = group_bcast<LPR>(tw[k][1], j);
-                const float w10 = group_bcast<LPR>(tw[k][2], j);
-                const float w11 = group_bcast<LPR>(tw[k][3], j);
-                const int r0 = group_bcast<LPR>(tr0[k], j);
-                const int r1x = group_bcast<LPR>(tr1[k], j);
-                const size_t dwo = (r1x < 0) ? row_elems : 0;
-                const T *p00 = base + (size_t)r0 * row_elems;
-                const T *p10 = base + (size_t)(r1x & 0x7fffffff) * row_elems;
-                float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-                RowVec<T>::load(p00, v00);
-                RowVec<T>::load(p00 + dwo, v01);
-                RowVec<T>::load(p10, v10);
-                RowVec<T>::load(p10 + dwo, v11);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    acc[e] = fmaf(w00, v00[e], acc[e]);
-                    acc[e] = fmaf(w01, v01[e], acc[e]);
-                    acc[e] = fmaf(w10, v10[e], acc[e]);
-                    acc[e] = fmaf(w11, v11[e], acc[e]);
+            for (int k = 0; k < NSL; ++k) {
+                const int s = sub + k * LPR;
+                tw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tr[k] = make_int2(0, 0);
+                if (s < LP && active) {
+                    const size_t t = (size_t)pair * LP + s;
+                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
+                    const float a = __ldg(attn + t);
+                    const int l = s / P;
+                    const TapGeom g = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
+                    tw[k] = masked_weights(g, a);
+                    tr[k] = make_int2(g.r0, g.r1 | (g.dw << 31));
                 }
             }
+
+            // ---- stage 2: gather rows for this lane's channel slice ----
+            const unsigned char *base = reinterpret_cast<const unsigned char *>(
+                value + ((size_t)b * S * M + m) * D + (size_t)sub * VEC);
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NSL; ++k) {
+                __syncwarp();                      // previous records fully consumed
+                slab.put(sub, tw[k], tr[k]);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < LPR; ++j) {
+                    const float4 w = slab.weights(j);
+                    const int2 rr = slab.rows(j);
+                    const unsigned dwo = (rr.y < 0) ? row_bytes : 0u;
+                    const unsigned char *p0 = base + (unsigned long long)(unsigned)rr.x * row_bytes;
+                    const unsigned char *p1 = base + (unsigned long long)(unsigned)(rr.y & 0x7fffffff) * row_bytes;
+                    float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+                    RowVec<T>::load(reinterpret_cast<const T *>(p0), v00);
+                    RowVec<T>::load(reinterpret_cast<const T *>(p0 + dwo), v01);
+                    RowVec<T>::load(reinterpret_cast<const T *>(p1), v10);
+                    RowVec<T>::load(reinterpret_cast<const T *>(p1 + dwo), v11);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        acc[e] = fmaf(w.x, v00[e], acc[e]);
+                        acc[e] = fmaf(w.y, v01[e], acc[e]);
+                        acc[e] = fmaf(w.z, v10[e], acc[e]);
+                        acc[e] = fmaf(w.w, v11[e], acc[e]);
+                    }
+                }
+            }
+            if (active) RowVec<T>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
         }
-        if (active) RowVec<T>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
     }
 }
 
 // Shuffle reduce-scatter inside a group of LPR lanes: on entry part[j][c] is this lane's partial sum for tap j,
-// corner c; on exit res[c] is the full group sum for tap `sub`.  LPR-1 rounds of 4*LPR/2^r shuffles.
+// corner c; on exit res[c] is the full group sum for tap `sub`.  log2(LPR) rounds, 4*LPR/2^r shuffles in round r.
 template <int LPR>
 __device__ __forceinline__ void group_reduce_scatter(float (&part)[LPR][4], int sub, float (&res)[4]) {
 #pragma unroll
@@ -159,122 +254,122 @@ __device__ __forceinline__ void group_reduce_scatter(float (&part)[LPR][4], int 
 // Per tap only the four corner dot products  dot_k = sum_c g[c] * V_k[c]  cross lanes; the bilinear coefficients are
 // applied afterwards by the single lane that owns the tap.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int D, int LP_MAX>
-__global__ void __launch_bounds__(kTiledThreads)
+template <typename T, int D, int LP_MAX, int MIN_CTAS>
+__global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
-               int S, int M, int L, int Lq, int P, long long npairs, int pairs_per_cta,
+               int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn)
 {
     constexpr int VEC = RowVec<T>::kElems;
     constexpr int LPR = D / VEC;
     constexpr int GPW = 32 / LPR;
     constexpr int NSL = LP_MAX / LPR;
+    constexpr int ITERS = kTileSlots / (kTiledWarps * GPW);
     static_assert(D % VEC == 0 && (LPR & (LPR - 1)) == 0 && LPR <= 32 && LP_MAX % LPR == 0, "bad tiling");
 
-    __shared__ LevelSmem lv;
-    load_levels(lv, shapes, lsi, L);
+    __shared__ WorkMap wm;
+    __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
     const int LP = L * P;
-    const size_t row_elems = (size_t)M * D;
-    const long long cta_begin = (long long)blockIdx.x * pairs_per_cta;
-    const long long cta_end = min(npairs, cta_begin + (long long)pairs_per_cta);
+    const unsigned row_elems = (unsigned)(M * D);
+    TapSlab<LPR> slab(slab_mem + warp * TapSlab<LPR>::kBytes, grp);
 
-    for (long long p0 = cta_begin + (long long)warp * GPW; p0 < cta_end; p0 += (long long)nwarps * GPW) {
-        const long long pair_raw = p0 + grp;
-        const bool active = pair_raw < cta_end;
-        const long long pair = active ? pair_raw : cta_end - 1;
-        const int m = (int)(pair % M);
-        const int b = (int)((pair / M) / Lq);
+    for (unsigned tile = blockIdx.x; tile < wm.ntiles; tile += gridDim.x) {
+        const TileCtx tc = decode_tile(wm, tile, L, M);
+#pragma unroll 1
+        for (int it = 0; it < ITERS; ++it) {
+            unsigned pair; int b, m;
+            const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
 
-        float g[VEC];
-        RowVec<T>::load(grad_out + (size_t)pair * D + (size_t)sub * VEC, g);
+            float g[VEC];
+            RowVec<T>::load(grad_out + (size_t)pair * D + (size_t)sub * VEC, g);
 
-        // ---- stage 1 ----
-        float tw[NSL][4], tlh[NSL], tlw[NSL], ta[NSL];
-        int tr0[NSL], tr1[NSL], tl[NSL];
-        unsigned tm[NSL];
+            // ---- stage 1 ----
+            float4 tw[NSL];
+            int2 tr[NSL];
+            float tlh[NSL], tlw[NSL], ta[NSL];
+            unsigned tmeta[NSL];                 // corner mask | level << 4
 #pragma unroll
-        for (int k = 0; k < NSL; ++k) {
-            const int s = sub + k * LPR;
-            tw[k][0] = tw[k][1] = tw[k][2] = tw[k][3] = 0.f;
-            tr0[k] = 0; tr1[k] = 0; tl[k] = 0; tm[k] = 0; tlh[k] = 0.f; tlw[k] = 0.f; ta[k] = 0.f;
-            if (s < LP && active) {
-                const long long t = pair * LP + s;
-                const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
-                const float a = __ldg(attn + t);
-                const int l = s / P;
-                const TapGeom gm = tap_geometry(xy.x, xy.y, lv.H[l], lv.W[l], lv.start[l]);
-                const float hh = 1.f - gm.lh, hw = 1.f - gm.lw;
-                tw[k][0] = (gm.mask & 1u) ? hh * hw * a : 0.f;
-                tw[k][1] = (gm.mask & 2u) ? hh * gm.lw * a : 0.f;
-                tw[k][2] = (gm.mask & 4u) ? gm.lh * hw * a : 0.f;
-                tw[k][3] = (gm.mask & 8u) ? gm.lh * gm.lw * a : 0.f;
-                tr0[k] = gm.r0;
-                tr1[k] = gm.r1 | (gm.dw << 31);
-                tl[k] = l; tm[k] = gm.mask; tlh[k] = gm.lh; tlw[k] = gm.lw; ta[k] = a;
-            }
-        }
-
-        const size_t slab = (size_t)b * S * row_elems + (size_t)m * D + (size_t)sub * VEC;
-        const T *base = value + slab;
-        float *gbase = grad_value + slab;
-
-        // ---- stage 2 ----
-#pragma unroll
-        for (int k = 0; k < NSL; ++k) {
-            float part[LPR][4];
-#pragma unroll
-            for (int j = 0; j < LPR; ++j) {
-                float w[4];
-                w[0] = group_bcast<LPR>(tw[k][0], j);
-                w[1] = group_bcast<LPR>(tw[k][1], j);
-                w[2] = group_bcast<LPR>(tw[k][2], j);
-                w[3] = group_bcast<LPR>(tw[k][3], j);
-                const int r0 = group_bcast<LPR>(tr0[k], j);
-                const int r1x = group_bcast<LPR>(tr1[k], j);
-                const size_t dwo = (r1x < 0) ? row_elems : 0;
-                size_t off[4];
-                off[0] = (size_t)r0 * row_elems;
-                off[1] = off[0] + dwo;
-                off[2] = (size_t)(r1x & 0x7fffffff) * row_elems;
-                off[3] = off[2] + dwo;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[VEC];
-                    RowVec<T>::load(base + off[c], v);
-                    float dsum = 0.f;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) dsum = fmaf(g[e], v[e], dsum);
-                    part[j][c] = dsum;
-                    if (w[c] != 0.f) {            // masked-out corners and idle groups carry weight 0
-#pragma unroll
-                        for (int e = 0; e < VEC; e += 4)
-                            red_add_v4(gbase + off[c] + e, w[c] * g[e], w[c] * g[e + 1], w[c] * g[e + 2], w[c] * g[e + 3]);
-                    }
+            for (int k = 0; k < NSL; ++k) {
+                const int s = sub + k * LPR;
+                tw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tr[k] = make_int2(0, 0);
+                tlh[k] = tlw[k] = ta[k] = 0.f; tmeta[k] = 0;
+                if (s < LP && active) {
+                    const size_t t = (size_t)pair * LP + s;
+                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
+                    const float a = __ldg(attn + t);
+                    const int l = s / P;
+                    const TapGeom gm = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
+                    tw[k] = masked_weights(gm, a);
+                    tr[k] = make_int2(gm.r0, gm.r1 | (gm.dw << 31));
+                    tlh[k] = gm.lh; tlw[k] = gm.lw; ta[k] = a; tmeta[k] = gm.mask | ((unsigned)l << 4);
                 }
             }
-            float dot[4];
-            group_reduce_scatter<LPR>(part, sub, dot);
 
-            // ---- the lane that owns tap (sub + k*LPR) finishes it ----
-            const int s = sub + k * LPR;
-            if (s < LP && active) {
-                const unsigned mk = tm[k];
-                const float d0 = (mk & 1u) ? dot[0] : 0.f, d1 = (mk & 2u) ? dot[1] : 0.f;
-                const float d2 = (mk & 4u) ? dot[2] : 0.f, d3 = (mk & 8u) ? dot[3] : 0.f;
-                const float lh = tlh[k], lw = tlw[k], hh = 1.f - lh, hw = 1.f - lw;
-                const float val = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;     // cuh:155-156
-                const float gw = hh * (d1 - d0) + lh * (d3 - d2);                                 // cuh:124,133,142,151
-                const float gh = hw * (d2 - d0) + lw * (d3 - d1);                                 // cuh:123,132,141,150
-                const long long t = pair * LP + s;
-                grad_attn[t] = val;
-                const float a = ta[k];
-                reinterpret_cast<float2 *>(grad_loc)[t] =
-                    make_float2((float)lv.W[tl[k]] * a * gw, (float)lv.H[tl[k]] * a * gh);        // cuh:157-158
+            const size_t slab_off = ((size_t)b * S * M + m) * D + (size_t)sub * VEC;
+            const T *base = value + slab_off;
+            float *gbase = grad_value + slab_off;
+
+            // ---- stage 2 ----
+#pragma unroll
+            for (int k = 0; k < NSL; ++k) {
+                __syncwarp();
+                slab.put(sub, tw[k], tr[k]);
+                __syncwarp();
+                float part[LPR][4];
+#pragma unroll
+                for (int j = 0; j < LPR; ++j) {
+                    const float4 w4 = slab.weights(j);
+                    const int2 rr = slab.rows(j);
+                    const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const unsigned dwo = (rr.y < 0) ? row_elems : 0u;
+                    unsigned long long off[4];
+                    off[0] = (unsigned long long)(unsigned)rr.x * row_elems;
+                    off[1] = off[0] + dwo;
+                    off[2] = (unsigned long long)(unsigned)(rr.y & 0x7fffffff) * row_elems;
+                    off[3] = off[2] + dwo;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[VEC];
+                        RowVec<T>::load(base + off[c], v);
+                        float dsum = 0.f;
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) dsum = fmaf(g[e], v[e], dsum);
+                        part[j][c] = dsum;
+                        if (w[c] != 0.f) {            // masked-out corners, dead taps and idle groups carry weight 0
+#pragma unroll
+                            for (int e = 0; e < VEC; e += 4)
+                                red_add_v4(gbase + off[c] + e, w[c] * g[e], w[c] * g[e + 1], w[c] * g[e + 2],
+                                           w[c] * g[e + 3]);
+                        }
+                    }
+                }
+                float dot[4];
+                group_reduce_scatter<LPR>(part, sub, dot);
+
+                // ---- the lane that owns tap (sub + k*LPR) finishes it ----
+                const int s = sub + k * LPR;
+                if (s < LP && active) {
+                    const unsigned mk = tmeta[k];
+                    const int l = (int)(mk >> 4);
+                    const float d0 = (mk & 1u) ? dot[0] : 0.f, d1 = (mk & 2u) ? dot[1] : 0.f;
+                    const float d2 = (mk & 4u) ? dot[2] : 0.f, d3 = (mk & 8u) ? dot[3] : 0.f;
+                    const float lh = tlh[k], lw = tlw[k], hh = 1.f - lh, hw = 1.f - lw;
+                    const float val = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;   // cuh:155-156
+                    const float gw = hh * (d1 - d0) + lh * (d3 - d2);                               // cuh:124,133,142,151
+                    const float gh = hw * (d2 - d0) + lw * (d3 - d1);                               // cuh:123,132,141,150
+                    const size_t t = (size_t)pair * LP + s;
+                    grad_attn[t] = val;
+                    const float a = ta[k];
+                    reinterpret_cast<float2 *>(grad_loc)[t] =
+                        make_float2((float)wm.W[l] * a * gw, (float)wm.H[l] * a * gh);              // cuh:157-158
+                }
             }
         }
     }
