@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frames", action="store_true", help="skip the whole-model frames/s measurement")
+    ap.add_argument("--frames-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="target CPU seconds for the cpu_baseline sample")
     return ap.parse_args()
 
@@ -241,6 +243,10 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(MSDA, calls, op_args, world, smp_step, args.e2e_steps, device, barrier)
 
+    frames = None
+    if not args.no_frames:
+        frames = run_frames(cfg, world, rank, device, args.frames_steps, barrier, lib)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(cfg, args.cpu_budget_s)
@@ -261,13 +267,59 @@ def run_b200(args):
                                "enc_bwd": round(cfg.samples("enc") / kern["enc_bwd_ms"] / 1e6, 2),
                                "dec_fwd": round(cfg.samples("dec") / kern["dec_fwd_ms"] / 1e6, 2),
                                "dec_bwd": round(cfg.samples("dec") / kern["dec_bwd_ms"] / 1e6, 2)},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "frames": frames, "gpu_launches": int(launches), "clocks": clocks,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def run_frames(cfg, world, rank, device, steps, barrier, lib):
+    """Whole-model frames/s: one training step of the 6-encoder + 6-decoder-layer deformable transformer (fwd + bwd,
+    fp32, d_model 256, d_ffn 2048) on synthetic multi-scale features of the workload's shape; frames sharded over ranks,
+    ONE flat NCCL all-reduce of all parameter gradients per step.  Backbone, heads, matcher and losses are excluded."""
+    from uninext_b200.dp import FlatGradBucket
+    from uninext_b200.modules.deformable_layers import DeformableStack
+    from uninext_b200.workloads import level_tensors
+    torch.manual_seed(1234)                                   # identical weights on every rank
+    model = DeformableStack(num_layers=6, num_queries=cfg.dec_queries).to(device)
+    bucket = FlatGradBucket(model.parameters())
+    shapes = cfg.shapes
+    ss, lsi = level_tensors(shapes, device)
+    g = torch.Generator(device=device).manual_seed(77 + rank)
+    src = torch.randn(cfg.batch, cfg.S, 256, device=device, generator=g)
+    pos = torch.randn(cfg.batch, cfg.S, 256, device=device, generator=g)
+
+    def train_step():
+        bucket.zero_()
+        out = model(src, pos, shapes, ss, lsi)
+        out.square().mean().backward()
+        bucket.all_reduce_mean()
+
+    for _ in range(3):
+        train_step()
+    barrier()
+    l0 = lib.msda_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        train_step()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= steps
+    return {"frames_per_s": round(world * cfg.batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 3), "steps": steps,
+            "frames_per_gpu": cfg.batch, "msda_launches_per_step": int((lib.msda_launch_count() - l0) / steps),
+            "grad_allreduce_bytes": bucket.nbytes,
+            "what": "6 enc + 6 dec deformable transformer layers fwd+bwd (fp32) + one flat gradient all-reduce; "
+                    "synthetic features, backbone/heads/losses excluded"}
 
 
 def run_e2e(MSDA, calls, op_args, world, smp_step, steps, device, barrier):

@@ -1,0 +1,104 @@
+"""The callers of the op: encoder / decoder layers of the deformable transformer, with the reference's sub-module
+names so its checkpoints load unchanged (deformable_transformer.py:321-361 encoder layer, :364-416 decoder layer),
+plus ``DeformableStack`` -- 6 + 6 layers wired the way the reference transformer wires them
+(reference points: deformable_transformer.py:280-292; decoder boxes as 4-d reference points: :457-465) -- which is the
+unit of the whole-model frames/s measurement (backbone, heads, matcher and losses are outside the hot path).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .ms_deform_attn import MSDeformAttn
+
+
+def _add_pos(x, pos):
+    return x if pos is None else x + pos
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, op_dtype=op_dtype)
+        self.dropout1, self.norm1 = nn.Dropout(dropout), nn.LayerNorm(d_model)
+        self.linear1, self.dropout2 = nn.Linear(d_model, d_ffn), nn.Dropout(dropout)
+        self.linear2, self.dropout3 = nn.Linear(d_ffn, d_model), nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        att = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        src = self.norm1(src + self.dropout1(att))
+        ffn = self.linear2(self.dropout2(torch.relu(self.linear1(src))))
+        return self.norm2(src + self.dropout3(ffn))
+
+
+class DeformableTransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+        super().__init__()
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, op_dtype=op_dtype)
+        self.dropout1, self.norm1 = nn.Dropout(dropout), nn.LayerNorm(d_model)
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout2, self.norm2 = nn.Dropout(dropout), nn.LayerNorm(d_model)
+        self.linear1, self.dropout3 = nn.Linear(d_model, d_ffn), nn.Dropout(dropout)
+        self.linear2, self.dropout4 = nn.Linear(d_ffn, d_model), nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
+                src_padding_mask=None):
+        qk = _add_pos(tgt, query_pos).transpose(0, 1)
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1))[0].transpose(0, 1)
+        tgt = self.norm2(tgt + self.dropout2(sa))
+        ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes, level_start_index,
+                             src_padding_mask)
+        tgt = self.norm1(tgt + self.dropout1(ca))
+        ffn = self.linear2(self.dropout3(torch.relu(self.linear1(tgt))))
+        return self.norm3(tgt + self.dropout4(ffn))
+
+
+def encoder_reference_points(spatial_shapes_list, valid_ratios, device):
+    """Pixel centres of every level, normalised and scaled by the valid ratios -> [N, S, L, 2]
+    (deformable_transformer.py:280-292)."""
+    pts = []
+    for lvl, (h, w) in enumerate(spatial_shapes_list):
+        ys = torch.arange(h, dtype=torch.float32, device=device) + 0.5
+        xs = torch.arange(w, dtype=torch.float32, device=device) + 0.5
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        y = yy.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
+        x = xx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
+        pts.append(torch.stack((x, y), -1))
+    ref = torch.cat(pts, 1)
+    return ref[:, :, None] * valid_ratios[:, None]
+
+
+class DeformableStack(nn.Module):
+    """num_layers encoder layers over the flattened pyramid + num_layers decoder layers over `num_queries` box queries
+    (UNINEXT defaults: d_model 256, d_ffn 2048, 8 heads, 4 levels, 4 points; uninext/config.py:156-174)."""
+
+    def __init__(self, d_model=256, d_ffn=2048, n_heads=8, n_levels=4, n_points=4, num_layers=6, num_queries=300,
+                 dropout=0.0, op_dtype=None):
+        super().__init__()
+        kw = dict(d_model=d_model, d_ffn=d_ffn, dropout=dropout, n_levels=n_levels, n_heads=n_heads,
+                  n_points=n_points, op_dtype=op_dtype)
+        self.encoder = nn.ModuleList(DeformableTransformerEncoderLayer(**kw) for _ in range(num_layers))
+        self.decoder = nn.ModuleList(DeformableTransformerDecoderLayer(**kw) for _ in range(num_layers))
+        self.level_embed = nn.Parameter(torch.randn(n_levels, d_model) * 0.02)
+        self.query_embed = nn.Embedding(num_queries, d_model * 2)
+        self.reference_boxes = nn.Linear(d_model, 4)
+        self.n_levels = n_levels
+
+    def forward(self, src, pos, spatial_shapes_list, spatial_shapes, level_start_index):
+        """src, pos: [N, S, C] flattened multi-scale features / position encodings.  Returns decoder output [N, Q, C]."""
+        n = src.shape[0]
+        valid = torch.ones(n, self.n_levels, 2, device=src.device)
+        ref = encoder_reference_points(spatial_shapes_list, valid, src.device)
+        memory = src
+        for layer in self.encoder:
+            memory = layer(memory, pos, ref, spatial_shapes, level_start_index, None)
+        qpos, tgt = self.query_embed.weight.chunk(2, dim=-1)
+        qpos, tgt = qpos[None].expand(n, -1, -1), tgt[None].expand(n, -1, -1)
+        boxes = self.reference_boxes(qpos).sigmoid()                                     # [N, Q, 4] (cx, cy, w, h)
+        ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
+        out = tgt
+        for layer in self.decoder:
+            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None)
+        return out

@@ -1,0 +1,103 @@
+"""``MSDeformAttn`` -- the nn.Module around the op, API- and checkpoint-compatible with the reference
+(ops/modules/ms_deform_attn.py:30-116): same constructor, same four Linear sub-modules and parameter names
+(``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj`` -- the optimiser selects
+``sampling_offsets`` by name, train_net.py:163-164), same initialisation, same forward signature and maths.
+
+``op_dtype=torch.bfloat16`` (new) stores value / output in bf16 for the op (fp32 sampling locations and attention
+weights, fp32 accumulation); the default reproduces the reference's fp32 behaviour, including the fp32 cast under
+autocast (ms_deform_attn.py:78).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from uninext_b200.functions import MSDeformAttnFunction, MSDeformAttnFunctionBF16
+
+
+def _power_of_two(n: int) -> bool:
+    if not isinstance(n, int) or n < 0:
+        raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+        super().__init__()
+        if d_model % n_heads:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        if not _power_of_two(d_model // n_heads):
+            warnings.warn("MSDeformAttn: a power-of-two head dimension is what the tiled sm_100a kernels cover; "
+                          "other sizes run on the generic kernel.")
+        self.im2col_step = 64                     # accepted for drop-in compatibility (ms_deform_attn.py:48)
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        self.op_dtype = op_dtype
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Reference scheme (ms_deform_attn.py:62-76): zero offset/weight matrices; offset bias = a ring of directions,
+        head k pointing at angle 2*pi*k/M (max-norm normalised), point p at distance p+1; Xavier projections."""
+        with torch.no_grad():
+            self.sampling_offsets.weight.zero_()
+            ang = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+            ring = torch.stack((ang.cos(), ang.sin()), dim=-1)
+            ring = ring / ring.abs().amax(dim=-1, keepdim=True)
+            dist = torch.arange(1, self.n_points + 1, dtype=torch.float32)
+            bias = ring[:, None, None, :] * dist[None, None, :, None]                    # [M, 1, P, 2]
+            self.sampling_offsets.bias.copy_(bias.expand(-1, self.n_levels, -1, -1).reshape(-1))
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
+            nn.init.xavier_uniform_(self.value_proj.weight)
+            self.value_proj.bias.zero_()
+            nn.init.xavier_uniform_(self.output_proj.weight)
+            self.output_proj.bias.zero_()
+
+    def sampling_locations(self, offsets, reference_points, input_spatial_shapes):
+        """offsets [N,Lq,M,L,P,2] (pixels) -> normalised locations (ms_deform_attn.py:103-112)."""
+        ref = reference_points[:, :, None, :, None, :]
+        if reference_points.shape[-1] == 2:
+            wh = input_spatial_shapes.flip(-1).to(offsets.dtype)                          # (W_l, H_l)
+            return ref + offsets / wh[None, None, None, :, None, :]
+        if reference_points.shape[-1] == 4:
+            return ref[..., :2] + offsets / self.n_points * ref[..., 2:] * 0.5
+        raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
+
+    def _forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                 input_padding_mask):
+        n, lq, _ = query.shape
+        s = input_flatten.shape[1]
+        m, l, p = self.n_heads, self.n_levels, self.n_points
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        value = value.view(n, s, m, self.d_model // m)
+        offsets = self.sampling_offsets(query).view(n, lq, m, l, p, 2)
+        weights = F.softmax(self.attention_weights(query).view(n, lq, m, l * p), dim=-1).view(n, lq, m, l, p)
+        loc = self.sampling_locations(offsets, reference_points, input_spatial_shapes)
+        if self.op_dtype == torch.bfloat16:
+            out = MSDeformAttnFunctionBF16.apply(value, input_spatial_shapes, input_level_start_index, loc, weights,
+                                                 self.im2col_step).to(query.dtype)
+        else:
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
+                                             weights.contiguous(), self.im2col_step)
+        return self.output_proj(out)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """query [N,Lq,C]; reference_points [N,Lq,L,2|4]; input_flatten [N,S,C]; returns [N,Lq,C]."""
+        if self.op_dtype is None and torch.is_autocast_enabled():
+            # reference: @custom_fwd(cast_inputs=float32) on forward (ms_deform_attn.py:78)
+            with torch.autocast("cuda", enabled=False):
+                f = lambda t: t.float() if t.is_floating_point() else t
+                return self._forward(f(query), f(reference_points), f(input_flatten), input_spatial_shapes,
+                                     input_level_start_index, input_padding_mask)
+        return self._forward(query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                             input_padding_mask)
