@@ -70,6 +70,14 @@ int allow_patches() {
     return v;
 }
 
+// TMA staging of (x, y, a): linear slot order only, and every pair's tap run must start 16-byte aligned (L*P % 4 == 0).
+// MSDA_NO_TMA=1 switches it off (A/B measurements).
+bool use_tma_staging(const Dims &d) {
+    static int off = -1;
+    if (off < 0) { const char *e = getenv("MSDA_NO_TMA"); off = (e && e[0] == '1') ? 1 : 0; }
+    return !off && !allow_patches() && ((d.L * d.P) % 4 == 0);
+}
+
 constexpr int kFwdMinCtas = 4, kBwdMinCtas = 2;     // r01d sweep: fwd flat for 3..5, bwd best at 2 (128 regs, no spills)
 
 int env_int(const char *name, int dflt) {
@@ -77,31 +85,23 @@ int env_int(const char *name, int dflt) {
     return (e && e[0]) ? atoi(e) : dflt;
 }
 
+template <typename T> struct FwdVec { static constexpr int v = 16 / sizeof(T); };      // 16-byte row slices
+template <typename T> struct BwdVec { static constexpr int v = 4; };                  // 4 channels per lane (see RowVec)
+
 template <typename T, int D, int LP_MAX>
 cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                        const Dims &d, T *out, cudaStream_t st) {
-    auto kern = msda::msda_fwd_tiled<T, D, LP_MAX, kFwdMinCtas>;
-    static int slots = resident_ctas(kern);
-#ifdef MSDA_EXPERIMENTS
-    if constexpr (D == 32 && LP_MAX == 16) {
-        static const int want = env_int("MSDA_FWD_CTAS", kFwdMinCtas);
-        static bool once = false;
-        if (!once) {
-            once = true;
-            if (want == 1) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 1>; }
-            if (want == 2) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 2>; }
-            if (want == 3) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 3>; }
-            if (want == 5) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 5>; }
-            if (want == 6) { kern = msda::msda_fwd_tiled<T, D, LP_MAX, 6>; }
-            slots = resident_ctas(kern);
-            static auto chosen = kern; (void)chosen;
-        }
-        static auto kept = kern;
-        kern = kept;
-    }
-#endif
+    constexpr int VEC = FwdVec<T>::v;
+    constexpr bool kCanStage = (LP_MAX <= 16);          // per-warp double buffer must fit static shared memory
+    const bool tma = kCanStage && use_tma_staging(d);
+    auto kern = tma ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage>
+                    : msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false>;
+    static int slots_tma = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage>);
+    static int slots_ldg = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false>);
+    int slots = tma ? slots_tma : slots_ldg;
     const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
-    const unsigned tiles_ub = (npairs + msda::kTileSlots - 1) / msda::kTileSlots;      // linear order; patches >= this
+    constexpr unsigned kIterPairs = msda::kTiledWarps * (32 / (D / VEC));
+    const unsigned tiles_ub = (npairs + kIterPairs - 1) / kIterPairs;        // linear order (patch order has fewer, larger tiles)
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P, npairs,
                                                allow_patches(), out);
@@ -112,25 +112,17 @@ cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi
 template <typename T, int D, int LP_MAX>
 cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                        const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
-    auto kern = msda::msda_bwd_tiled<T, D, LP_MAX, kBwdMinCtas>;
-    static int slots = resident_ctas(kern);
-#ifdef MSDA_EXPERIMENTS
-    if constexpr (D == 32 && LP_MAX == 16) {
-        static const int want = env_int("MSDA_BWD_CTAS", kBwdMinCtas);
-        static bool once = false;
-        if (!once) {
-            once = true;
-            if (want == 1) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 1>; }
-            if (want == 2) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 2>; }
-            if (want == 4) { kern = msda::msda_bwd_tiled<T, D, LP_MAX, 4>; }
-            slots = resident_ctas(kern);
-        }
-        static auto kept = kern;
-        kern = kept;
-    }
-#endif
+    constexpr int VEC = BwdVec<T>::v;
+    constexpr bool kCanStage = (LP_MAX <= 16);
+    const bool tma = kCanStage && use_tma_staging(d);
+    auto kern = tma ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage>
+                    : msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false>;
+    static int slots_tma = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage>);
+    static int slots_ldg = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false>);
+    int slots = tma ? slots_tma : slots_ldg;
     const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
-    const unsigned tiles_ub = (npairs + msda::kTileSlots - 1) / msda::kTileSlots;
+    constexpr unsigned kIterPairs = msda::kTiledWarps * (32 / (D / VEC));
+    const unsigned tiles_ub = (npairs + kIterPairs - 1) / kIterPairs;
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
                                                npairs, allow_patches(), gv, gl, ga);

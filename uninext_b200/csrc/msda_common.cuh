@@ -53,10 +53,12 @@ __device__ __forceinline__ TapGeom tap_geometry(float x, float y, int H, int W, 
     return g;
 }
 
-// 16-byte vector access to one slice of a value / grad row, widened to fp32 registers.
-template <typename T> struct RowVec;
+// Vector access to one slice of a value / grad row, widened to fp32 registers.  VEC = elements per lane:
+// fp32: 4 (16 bytes); bf16: 8 (16 bytes, forward) or 4 (8 bytes, backward -- keeps one lane's grad_value slice a
+// contiguous 16-byte fp32 quad so that every red.v4 fills whole sectors).
+template <typename T, int VEC> struct RowVec;
 
-template <> struct RowVec<float> {
+template <> struct RowVec<float, 4> {
     static constexpr int kElems = 4;
     __device__ static __forceinline__ void load(const float *p, float (&v)[4]) {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
@@ -67,7 +69,21 @@ template <> struct RowVec<float> {
     }
 };
 
-template <> struct RowVec<__nv_bfloat16> {
+template <> struct RowVec<__nv_bfloat16, 4> {
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    __device__ static __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const unsigned *>(&a),
+                                                   *reinterpret_cast<const unsigned *>(&b));
+    }
+};
+
+template <> struct RowVec<__nv_bfloat16, 8> {
     static constexpr int kElems = 8;
     __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
         const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));

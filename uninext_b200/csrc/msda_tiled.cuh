@@ -13,9 +13,9 @@
 // (cuh:347-401): the backward channel reduction is a shuffle reduce-scatter that leaves tap j's sums on lane j,
 // i.e. on the lane that already holds that tap's geometry.
 //
-// Work decomposition.  The grid is persistent (SM count x resident CTAs); CTA c walks tiles c, c+G, c+2G, ... of 64
-// (pair) slots.  Two slot orders:
-//   linear  -- slots are consecutive pairs in memory order (decoder-style calls: queries have no spatial structure);
+// Work decomposition.  The grid is persistent (SM count x resident CTAs); CTA c walks tiles c, c+G, c+2G, ...
+// Two slot orders:
+//   linear  -- a tile is one CTA iteration of consecutive pairs in memory order (the default);
 //   patches -- used when Lq == S and the level table tiles [0, S) exactly, i.e. queries ARE the pixels of the pyramid
 //              (encoder self-attention, deformable_transformer.py:280-292): a tile is one head of an 8x8 pixel patch,
 //              so the rows gathered by neighbouring queries of the same head overlap in L1 while the tile is resident.
@@ -37,11 +37,13 @@ struct WorkMap {
     int pfirst[kMaxLevels + 1];      // first patch index of level l within one batch element
     int patches;                     // 1 when the patch order is in use
     unsigned ntiles;
+    unsigned linear_tile;            // pairs per tile in linear order (= one CTA iteration)
 };
 
 // Every CTA derives the same map from the (device-resident) level table: no host read of spatial_shapes is needed.
 __device__ __forceinline__ void build_work_map(WorkMap &wm, const int64_t *shapes, const int64_t *lsi, int L, int N,
-                                               int S, int Lq, int M, unsigned npairs, int allow_patches) {
+                                               int S, int Lq, int M, unsigned npairs, int allow_patches,
+                                               unsigned linear_tile) {
     if (threadIdx.x == 0) {
         int run = 0, np = 0;
         bool tiled = (Lq == S) && allow_patches;
@@ -57,7 +59,8 @@ __device__ __forceinline__ void build_work_map(WorkMap &wm, const int64_t *shape
         wm.pfirst[L] = np;
         tiled = tiled && (run == S);
         wm.patches = tiled ? 1 : 0;
-        wm.ntiles = tiled ? (unsigned)N * (unsigned)M * (unsigned)np : (npairs + kTileSlots - 1) / kTileSlots;
+        wm.ntiles = tiled ? (unsigned)N * (unsigned)M * (unsigned)np : (npairs + linear_tile - 1) / linear_tile;
+        wm.linear_tile = linear_tile;
     }
     __syncthreads();
 }
@@ -84,7 +87,7 @@ __device__ __forceinline__ TileCtx decode_tile(const WorkMap &wm, unsigned tile,
         t.base_pair = 0;
     } else {
         t.b = t.m = t.H = t.W = t.start = t.py0 = t.px0 = 0;
-        t.base_pair = tile * kTileSlots;
+        t.base_pair = tile * wm.linear_tile;
     }
     return t;
 }
@@ -101,7 +104,7 @@ __device__ __forceinline__ bool slot_pair(const WorkMap &wm, const TileCtx &t, i
         pair = ((unsigned)t.b * (unsigned)Lq + (unsigned)q) * (unsigned)M + (unsigned)t.m;
         return ok;
     }
-    const unsigned p = t.base_pair + (unsigned)(it * kTiledWarps * GPW + warp * GPW + grp);
+    const unsigned p = t.base_pair + (unsigned)(warp * GPW + grp);        // linear tiles are a single iteration
     const bool ok = p < npairs;
     pair = ok ? p : npairs - 1;
     m = (int)(pair % (unsigned)M);
@@ -128,6 +131,44 @@ struct TapSlab {
     __device__ __forceinline__ int2 rows(int j) const { return *reinterpret_cast<const int2 *>(r + j * 8); }
 };
 
+
+// ---- TMA (bulk async copy) staging of one warp-iteration's sampling locations and attention weights -----------------
+// Linear order only: the GPW pairs a warp handles in one iteration are consecutive in memory, so their taps are two
+// contiguous runs (GPW*LP*8 bytes of (x,y), GPW*LP*4 bytes of weights).  Lane 0 issues the two cp.async.bulk copies for
+// the NEXT iteration into the other stage of a per-warp double buffer and the warp waits on that stage's mbarrier when
+// it gets there: the taps arrive without occupying registers or issue slots, one iteration ahead of their use.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int GPW, int LP_MAX, bool ENABLED>
+struct TapStage {                       // per-warp double buffer
+    static constexpr int kLoc = GPW * LP_MAX * 8, kAttn = GPW * LP_MAX * 4;
+    static constexpr int kBytes = ENABLED ? 2 * (kLoc + kAttn) : 16;
+};
+
 __device__ __forceinline__ float4 masked_weights(const TapGeom &g, float a) {
     const float hh = 1.f - g.lh, hw = 1.f - g.lw;
     return make_float4((g.mask & 1u) ? hh * hw * a : 0.f, (g.mask & 2u) ? hh * g.lw * a : 0.f,
@@ -137,13 +178,12 @@ __device__ __forceinline__ float4 masked_weights(const TapGeom &g, float a) {
 // ------------------------------------------------------------------------------------------------------------
 // forward:  out[b,q,m,:] = sum_taps a * bilinear(value_l[b,:,m,:], x, y)            (reference cuh:237-299)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int D, int LP_MAX, int MIN_CTAS>
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
                int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches, T *__restrict__ out)
 {
-    constexpr int VEC = RowVec<T>::kElems;
     constexpr int LPR = D / VEC;            // lanes per row
     constexpr int GPW = 32 / LPR;           // (b,q,m) pairs in flight per warp
     constexpr int NSL = LP_MAX / LPR;       // taps resolved per lane
@@ -153,7 +193,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
 
     __shared__ WorkMap wm;
     __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
-    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches);
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches, kTiledWarps * GPW);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
@@ -161,12 +201,51 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const unsigned row_bytes = (unsigned)(M * D) * (unsigned)sizeof(T);
     TapSlab<LPR> slab(slab_mem + warp * TapSlab<LPR>::kBytes, grp);
 
+    // per-warp TMA double buffer for (x, y, a) -- linear order only (the host passes TMA=true only then)
+    using Stage = TapStage<GPW, LP_MAX, TMA>;
+    __shared__ __align__(128) unsigned char stage_mem[kTiledWarps * Stage::kBytes];
+    __shared__ __align__(8) unsigned long long stage_bar[kTiledWarps * 2];
+    unsigned char *my_stage = stage_mem + warp * Stage::kBytes;
+    unsigned long long *my_bar = stage_bar + warp * 2;
+    unsigned tma_iter = 0;
+    auto stage_issue = [&](unsigned tile, unsigned st) {          // lane 0: taps of this warp's slots in `tile` -> stage st
+        const unsigned first = tile * wm.linear_tile + (unsigned)(warp * GPW);
+        if (first < npairs) {
+            const unsigned n = min((unsigned)GPW, npairs - first);
+            const unsigned lb = n * (unsigned)LP * 8u, ab = n * (unsigned)LP * 4u;
+            unsigned char *dst = my_stage + st * (Stage::kLoc + Stage::kAttn);
+            mbar_expect_tx(my_bar + st, lb + ab);
+            bulk_g2s(dst, loc + (size_t)first * LP * 2, lb, my_bar + st);
+            bulk_g2s(dst + Stage::kLoc, attn + (size_t)first * LP, ab, my_bar + st);
+        }
+    };
+    if constexpr (TMA) {
+        if (lane == 0) {
+            mbar_init(my_bar, 1); mbar_init(my_bar + 1, 1);
+            mbar_fence_init();
+            if (blockIdx.x < wm.ntiles) stage_issue(blockIdx.x, 0);
+        }
+        __syncwarp();
+    }
+
     for (unsigned tile = blockIdx.x; tile < wm.ntiles; tile += gridDim.x) {
         const TileCtx tc = decode_tile(wm, tile, L, M);
+        const int iters = wm.patches ? ITERS : 1;
 #pragma unroll 1
-        for (int it = 0; it < ITERS; ++it) {
+        for (int it = 0; it < iters; ++it) {
             unsigned pair; int b, m;
             const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
+            const float2 *st_loc = nullptr; const float *st_attn = nullptr;
+            if constexpr (TMA) {
+                const unsigned st = tma_iter & 1u;
+                __syncwarp();                                  // everyone is done with the stage about to be refilled
+                if (lane == 0 && tile + gridDim.x < wm.ntiles) stage_issue(tile + gridDim.x, st ^ 1u);
+                if (tile * wm.linear_tile + (unsigned)(warp * GPW) < npairs) mbar_wait(my_bar + st, (tma_iter >> 1) & 1u);
+                const unsigned char *src = my_stage + st * (Stage::kLoc + Stage::kAttn);
+                st_loc = reinterpret_cast<const float2 *>(src) + grp * LP;
+                st_attn = reinterpret_cast<const float *>(src + Stage::kLoc) + grp * LP;
+                ++tma_iter;
+            }
 
             // ---- stage 1: this lane resolves its taps (dead taps: zero weight, row 0) ----
             float4 tw[NSL];
@@ -178,8 +257,8 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                 tr[k] = make_int2(0, 0);
                 if (s < LP && active) {
                     const size_t t = (size_t)pair * LP + s;
-                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
-                    const float a = __ldg(attn + t);
+                    const float2 xy = TMA ? st_loc[s] : __ldg(reinterpret_cast<const float2 *>(loc) + t);
+                    const float a = TMA ? st_attn[s] : __ldg(attn + t);
                     const int l = s / P;
                     const TapGeom g = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
                     tw[k] = masked_weights(g, a);
@@ -206,10 +285,10 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                     const unsigned char *p0 = base + (unsigned long long)(unsigned)rr.x * row_bytes;
                     const unsigned char *p1 = base + (unsigned long long)(unsigned)(rr.y & 0x7fffffff) * row_bytes;
                     float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-                    RowVec<T>::load(reinterpret_cast<const T *>(p0), v00);
-                    RowVec<T>::load(reinterpret_cast<const T *>(p0 + dwo), v01);
-                    RowVec<T>::load(reinterpret_cast<const T *>(p1), v10);
-                    RowVec<T>::load(reinterpret_cast<const T *>(p1 + dwo), v11);
+                    RowVec<T, VEC>::load(reinterpret_cast<const T *>(p0), v00);
+                    RowVec<T, VEC>::load(reinterpret_cast<const T *>(p0 + dwo), v01);
+                    RowVec<T, VEC>::load(reinterpret_cast<const T *>(p1), v10);
+                    RowVec<T, VEC>::load(reinterpret_cast<const T *>(p1 + dwo), v11);
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
                         acc[e] = fmaf(w.x, v00[e], acc[e]);
@@ -219,7 +298,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                     }
                 }
             }
-            if (active) RowVec<T>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
+            if (active) RowVec<T, VEC>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
         }
     }
 }
@@ -254,7 +333,7 @@ __device__ __forceinline__ void group_reduce_scatter(float (&part)[LPR][4], int 
 // Per tap only the four corner dot products  dot_k = sum_c g[c] * V_k[c]  cross lanes; the bilinear coefficients are
 // applied afterwards by the single lane that owns the tap.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int D, int LP_MAX, int MIN_CTAS>
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
@@ -262,7 +341,6 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn)
 {
-    constexpr int VEC = RowVec<T>::kElems;
     constexpr int LPR = D / VEC;
     constexpr int GPW = 32 / LPR;
     constexpr int NSL = LP_MAX / LPR;
@@ -271,7 +349,7 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
 
     __shared__ WorkMap wm;
     __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
-    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches);
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches, kTiledWarps * GPW);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
@@ -279,15 +357,54 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
     const unsigned row_elems = (unsigned)(M * D);
     TapSlab<LPR> slab(slab_mem + warp * TapSlab<LPR>::kBytes, grp);
 
+    // per-warp TMA double buffer for (x, y, a) -- linear order only (the host passes TMA=true only then)
+    using Stage = TapStage<GPW, LP_MAX, TMA>;
+    __shared__ __align__(128) unsigned char stage_mem[kTiledWarps * Stage::kBytes];
+    __shared__ __align__(8) unsigned long long stage_bar[kTiledWarps * 2];
+    unsigned char *my_stage = stage_mem + warp * Stage::kBytes;
+    unsigned long long *my_bar = stage_bar + warp * 2;
+    unsigned tma_iter = 0;
+    auto stage_issue = [&](unsigned tile, unsigned st) {          // lane 0: taps of this warp's slots in `tile` -> stage st
+        const unsigned first = tile * wm.linear_tile + (unsigned)(warp * GPW);
+        if (first < npairs) {
+            const unsigned n = min((unsigned)GPW, npairs - first);
+            const unsigned lb = n * (unsigned)LP * 8u, ab = n * (unsigned)LP * 4u;
+            unsigned char *dst = my_stage + st * (Stage::kLoc + Stage::kAttn);
+            mbar_expect_tx(my_bar + st, lb + ab);
+            bulk_g2s(dst, loc + (size_t)first * LP * 2, lb, my_bar + st);
+            bulk_g2s(dst + Stage::kLoc, attn + (size_t)first * LP, ab, my_bar + st);
+        }
+    };
+    if constexpr (TMA) {
+        if (lane == 0) {
+            mbar_init(my_bar, 1); mbar_init(my_bar + 1, 1);
+            mbar_fence_init();
+            if (blockIdx.x < wm.ntiles) stage_issue(blockIdx.x, 0);
+        }
+        __syncwarp();
+    }
+
     for (unsigned tile = blockIdx.x; tile < wm.ntiles; tile += gridDim.x) {
         const TileCtx tc = decode_tile(wm, tile, L, M);
+        const int iters = wm.patches ? ITERS : 1;
 #pragma unroll 1
-        for (int it = 0; it < ITERS; ++it) {
+        for (int it = 0; it < iters; ++it) {
             unsigned pair; int b, m;
             const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
+            const float2 *st_loc = nullptr; const float *st_attn = nullptr;
+            if constexpr (TMA) {
+                const unsigned st = tma_iter & 1u;
+                __syncwarp();                                  // everyone is done with the stage about to be refilled
+                if (lane == 0 && tile + gridDim.x < wm.ntiles) stage_issue(tile + gridDim.x, st ^ 1u);
+                if (tile * wm.linear_tile + (unsigned)(warp * GPW) < npairs) mbar_wait(my_bar + st, (tma_iter >> 1) & 1u);
+                const unsigned char *src = my_stage + st * (Stage::kLoc + Stage::kAttn);
+                st_loc = reinterpret_cast<const float2 *>(src) + grp * LP;
+                st_attn = reinterpret_cast<const float *>(src + Stage::kLoc) + grp * LP;
+                ++tma_iter;
+            }
 
             float g[VEC];
-            RowVec<T>::load(grad_out + (size_t)pair * D + (size_t)sub * VEC, g);
+            RowVec<T, VEC>::load(grad_out + (size_t)pair * D + (size_t)sub * VEC, g);
 
             // ---- stage 1 ----
             float4 tw[NSL];
@@ -302,8 +419,8 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                 tlh[k] = tlw[k] = ta[k] = 0.f; tmeta[k] = 0;
                 if (s < LP && active) {
                     const size_t t = (size_t)pair * LP + s;
-                    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + t);
-                    const float a = __ldg(attn + t);
+                    const float2 xy = TMA ? st_loc[s] : __ldg(reinterpret_cast<const float2 *>(loc) + t);
+                    const float a = TMA ? st_attn[s] : __ldg(attn + t);
                     const int l = s / P;
                     const TapGeom gm = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
                     tw[k] = masked_weights(gm, a);
@@ -337,7 +454,7 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float v[VEC];
-                        RowVec<T>::load(base + off[c], v);
+                        RowVec<T, VEC>::load(base + off[c], v);
                         float dsum = 0.f;
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) dsum = fmaf(g[e], v[e], dsum);

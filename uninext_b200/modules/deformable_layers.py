@@ -91,6 +91,10 @@ class DeformableStack(nn.Module):
         n = src.shape[0]
         valid = torch.ones(n, self.n_levels, 2, device=src.device)
         ref = encoder_reference_points(spatial_shapes_list, valid, src.device)
+        # per-level embedding added to the position encoding (deformable_transformer.py:193-195 lvl_pos_embed)
+        lvl = torch.cat([torch.full((h * w,), i, device=src.device, dtype=torch.long)
+                         for i, (h, w) in enumerate(spatial_shapes_list)])
+        pos = pos + self.level_embed[lvl][None]
         memory = src
         for layer in self.encoder:
             memory = layer(memory, pos, ref, spatial_shapes, level_start_index, None)
