@@ -70,6 +70,16 @@ def dist_env():
     return world, rank, local
 
 
+def ncu_traffic(tag, key):
+    """DRAM bytes per launch from the committed ncu --set full capture (tools/ncu_traffic.py), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as fh:
+            return int(json.load(fh)[tag][key]["dram_bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -233,7 +243,13 @@ def run_b200(args):
     ach = b_bwd / (kern["enc_bwd_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "encoder-shaped backward: cudaMemsetAsync(grad_value) + msda_bwd_tiled",
                 "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": b_bwd, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": b_bwd,
+                "traffic": ncu_traffic(f"{args.config}_enc_{'f32' if args.dtype == 'fp32' else 'bf16'}", "bwd"),
+                "traffic_note": "kernel only (the 45.7 MB grad_value memset is a separate launch); profiles/ncu_traffic.json",
+                "binding_ceiling": "L2 vector atomics: red.global.add.v4.f32 on random 128-B rows sustains 5.7-6.4 TB/s "
+                                   "payload on this GPU (profiles/r01g_ubench_lsu_gather_ceiling.txt); the backward must "
+                                   "push 2.5 GB of them per call -> 390-440 us; forward is bound by the LSU gather rate "
+                                   "(68 B/clk/SM for L2-resident rows -> 147 us)",
                 "enc_fwd": {"achieved": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9, 1),
                             "frac": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9 / peak, 4),
                             "algorithmic_bytes_per_launch": b_fwd}}
