@@ -91,6 +91,32 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value,
                        float *grad_value_f32, uint16_t *grad_value,
                        float *grad_sampling_loc, float *grad_attn_weight, void *stream);
 
+/* ---- callers of the op: one-pass fp32 kernels around the cuBLAS GEMMs --------
+ * msda_prologue_forward_f32: raw projection -> attention softmax + sampling locations in the op's layouts.
+ *   Replaces the five elementwise passes of ops/modules/ms_deform_attn.py:99-112.
+ *   proj [R, M*L*P*3]: columns [0, M*L*P*2) = sampling offsets ordered (m,l,p,xy) (ms_deform_attn.py:99),
+ *                      columns [M*L*P*2, M*L*P*3) = attention logits ordered (m, l*p) (ms_deform_attn.py:100);
+ *   ref  [R, L, refdim] reference points (refdim 2) or boxes (refdim 4) (ms_deform_attn.py:103-109); R = N*Lq;
+ *   loc  [R, M, L, P, 2], attn [R, M, L, P] outputs.  L*P <= 32.
+ * msda_prologue_backward_f32: gradient of the raw projection from grad_loc / grad_attn (reference points are
+ *   treated as constants).
+ * msda_colsum_f32: out[c] = sum_r x[r,c] (bias gradients); cols % 4 == 0; `out` is zero-filled by the callee.
+ * msda_add_layernorm_forward_f32 / msda_layernorm_backward_f32: y = LayerNorm(a + b) over the last dimension
+ *   (deformable_transformer.py:354-356,359); cols in {128, 256, 384, 512}; b and z may be NULL (z = a + b is needed by
+ *   the backward when b != NULL); dgamma / dbeta are zero-filled by the callee. */
+int msda_prologue_forward_f32(const float *proj, const float *ref, const int64_t *spatial_shapes,
+                              int64_t R, int M, int L, int P, int refdim, float *loc, float *attn, void *stream);
+int msda_prologue_backward_f32(const float *grad_loc, const float *grad_attn, const float *attn, const float *ref,
+                               const int64_t *spatial_shapes, int64_t R, int M, int L, int P, int refdim,
+                               float *grad_proj, void *stream);
+int msda_colsum_f32(const float *x, int64_t rows, int cols, float *out, void *stream);
+int msda_add_layernorm_forward_f32(const float *a, const float *b, const float *gamma, const float *beta,
+                                   int64_t rows, int cols, float eps, float *z, float *y, float *mean, float *rstd,
+                                   void *stream);
+int msda_layernorm_backward_f32(const float *dy, const float *z, const float *gamma, const float *mean,
+                                const float *rstd, int64_t rows, int cols, float *dz, float *dgamma, float *dbeta,
+                                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 
 #include "../../include/msda_b200.h"
 #include "msda_generic.cuh"
+#include "msda_module.cuh"
 #include "msda_tiled.cuh"
 
 namespace {
@@ -313,6 +314,115 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
         err = cudaGetLastError();
     }
     return (int)err;
+}
+
+
+}  // extern "C"
+
+// ---- callers of the op --------------------------------------------------------------------------------------------
+namespace {
+template <int G>
+cudaError_t prologue_fwd_launch(const float *proj, const float *ref, const int64_t *shapes, long long npairs, int M, int L,
+                                int P, int refdim, float *loc, float *attn, cudaStream_t st) {
+    const long long threads = npairs * G;
+    msda::msda_prologue_fwd<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(proj, ref, shapes, npairs, M, L, P, refdim, loc, attn);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <int G>
+cudaError_t prologue_bwd_launch(const float *gl, const float *ga, const float *attn, const float *ref, const int64_t *shapes,
+                                long long npairs, int M, int L, int P, int refdim, float *gp, cudaStream_t st) {
+    const long long threads = npairs * G;
+    msda::msda_prologue_bwd<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(gl, ga, attn, ref, shapes, npairs, M, L, P, refdim, gp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+int group_width(int LP) { return LP <= 4 ? 4 : LP <= 8 ? 8 : LP <= 16 ? 16 : 32; }
+}  // namespace
+
+extern "C" {
+
+int msda_prologue_forward_f32(const float *proj, const float *ref, const int64_t *spatial_shapes, int64_t R, int M, int L,
+                              int P, int refdim, float *loc, float *attn, void *stream) {
+    if (!proj || !ref || !spatial_shapes || !loc || !attn || R <= 0 || M <= 0 || L <= 0 || P <= 0 || L * P > 32 ||
+        (refdim != 2 && refdim != 4) || (long long)R * M * 32 >= (1ll << 40))
+        return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long np = (long long)R * M;
+    switch (group_width(L * P)) {
+        case 4: return (int)prologue_fwd_launch<4>(proj, ref, spatial_shapes, np, M, L, P, refdim, loc, attn, st);
+        case 8: return (int)prologue_fwd_launch<8>(proj, ref, spatial_shapes, np, M, L, P, refdim, loc, attn, st);
+        case 16: return (int)prologue_fwd_launch<16>(proj, ref, spatial_shapes, np, M, L, P, refdim, loc, attn, st);
+        default: return (int)prologue_fwd_launch<32>(proj, ref, spatial_shapes, np, M, L, P, refdim, loc, attn, st);
+    }
+}
+
+int msda_prologue_backward_f32(const float *grad_loc, const float *grad_attn, const float *attn, const float *ref,
+                               const int64_t *spatial_shapes, int64_t R, int M, int L, int P, int refdim,
+                               float *grad_proj, void *stream) {
+    if (!grad_loc || !grad_attn || !attn || !ref || !spatial_shapes || !grad_proj || R <= 0 || M <= 0 || L <= 0 || P <= 0 ||
+        L * P > 32 || (refdim != 2 && refdim != 4))
+        return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long np = (long long)R * M;
+    switch (group_width(L * P)) {
+        case 4: return (int)prologue_bwd_launch<4>(grad_loc, grad_attn, attn, ref, spatial_shapes, np, M, L, P, refdim, grad_proj, st);
+        case 8: return (int)prologue_bwd_launch<8>(grad_loc, grad_attn, attn, ref, spatial_shapes, np, M, L, P, refdim, grad_proj, st);
+        case 16: return (int)prologue_bwd_launch<16>(grad_loc, grad_attn, attn, ref, spatial_shapes, np, M, L, P, refdim, grad_proj, st);
+        default: return (int)prologue_bwd_launch<32>(grad_loc, grad_attn, attn, ref, spatial_shapes, np, M, L, P, refdim, grad_proj, st);
+    }
+}
+
+int msda_colsum_f32(const float *x, int64_t rows, int cols, float *out, void *stream) {
+    if (!x || !out || rows <= 0 || cols <= 0 || cols % 4 != 0 || !aligned16(x) || !aligned16(out)) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st);
+    if (err != cudaSuccess) return (int)err;
+    long long ctas = (long long)num_sms() * 4;
+    int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+    if (rows_per_cta < 16) rows_per_cta = 16;
+    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    msda::msda_colsum<<<grid, 256, 0, st>>>(x, rows, cols, rows_per_cta, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_add_layernorm_forward_f32(const float *a, const float *b, const float *gamma, const float *beta, int64_t rows,
+                                   int cols, float eps, float *z, float *y, float *mean, float *rstd, void *stream) {
+    if (!a || !gamma || !beta || !y || !mean || !rstd || rows <= 0 || (b != nullptr && z == nullptr)) return MSDA_E_BADARG;
+    if (cols != 128 && cols != 256 && cols != 384 && cols != 512) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    switch (cols / 128) {
+        case 1: msda::msda_add_layernorm_fwd<1><<<grid, 256, 0, st>>>(a, b, gamma, beta, rows, eps, z, y, mean, rstd); break;
+        case 2: msda::msda_add_layernorm_fwd<2><<<grid, 256, 0, st>>>(a, b, gamma, beta, rows, eps, z, y, mean, rstd); break;
+        case 3: msda::msda_add_layernorm_fwd<3><<<grid, 256, 0, st>>>(a, b, gamma, beta, rows, eps, z, y, mean, rstd); break;
+        default: msda::msda_add_layernorm_fwd<4><<<grid, 256, 0, st>>>(a, b, gamma, beta, rows, eps, z, y, mean, rstd); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_layernorm_backward_f32(const float *dy, const float *z, const float *gamma, const float *mean, const float *rstd,
+                                int64_t rows, int cols, float *dz, float *dgamma, float *dbeta, void *stream) {
+    if (!dy || !z || !gamma || !mean || !rstd || !dz || !dgamma || !dbeta || rows <= 0) return MSDA_E_BADARG;
+    if (cols != 128 && cols != 256 && cols != 384 && cols != 512) return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(dgamma, 0, sizeof(float) * (size_t)cols, st);
+    if (err == cudaSuccess) err = cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)cols, st);
+    if (err != cudaSuccess) return (int)err;
+    long long ctas = (long long)num_sms() * 4;
+    int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+    rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
+    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    switch (cols / 128) {
+        case 1: msda::msda_layernorm_bwd<1><<<grid, 256, 0, st>>>(dy, z, gamma, mean, rstd, rows, rows_per_cta, dz, dgamma, dbeta); break;
+        case 2: msda::msda_layernorm_bwd<2><<<grid, 256, 0, st>>>(dy, z, gamma, mean, rstd, rows, rows_per_cta, dz, dgamma, dbeta); break;
+        case 3: msda::msda_layernorm_bwd<3><<<grid, 256, 0, st>>>(dy, z, gamma, mean, rstd, rows, rows_per_cta, dz, dgamma, dbeta); break;
+        default: msda::msda_layernorm_bwd<4><<<grid, 256, 0, st>>>(dy, z, gamma, mean, rstd, rows, rows_per_cta, dz, dgamma, dbeta); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -1,0 +1,162 @@
+"""Autograd wrappers of the one-pass kernels around the op (include/msda_b200.h, "callers of the op").
+
+They keep the reference modules' parameters (same tensors, same state_dict) and only change how the arithmetic is
+scheduled: the GEMMs stay cuBLAS (torch.addmm / torch.mm), the elementwise / reduction passes around them run as
+single hand-written kernels.
+
+* ``sampling_prologue``   -- ms_deform_attn.py:99-112 (two Linears + softmax + location arithmetic) as one GEMM over the
+                            concatenated weights + one kernel writing loc/attn in the op's layouts.
+* ``linear_colsum``       -- nn.Linear whose bias gradient is one column-sum kernel instead of a generic reduce.
+* ``add_layer_norm``      -- ``LayerNorm(a + b)`` (deformable_transformer.py:354-356,359) forward and backward.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from uninext_b200 import _cabi
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def colsum(x2d: torch.Tensor) -> torch.Tensor:
+    """sum over rows of a contiguous fp32 [rows, cols] CUDA tensor (cols % 4 == 0)."""
+    rows, cols = x2d.shape
+    if cols % 4 or x2d.data_ptr() % 16:
+        return x2d.sum(0)
+    out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        _cabi.check(_cabi.load().msda_colsum_f32(x2d.data_ptr(), rows, cols, out.data_ptr(), _stream()), "msda_colsum_f32")
+    return out
+
+
+class _LinearColsum(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        ctx.save_for_backward(x2, weight)
+        ctx.xshape = x.shape
+        y = torch.addmm(bias, x2, weight.t())
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x2, weight = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1]).contiguous()
+        gx = torch.mm(g2, weight).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        gw = torch.mm(g2.t(), x2) if ctx.needs_input_grad[1] else None
+        gb = colsum(g2) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+def linear_colsum(x, linear: torch.nn.Linear):
+    """``linear(x)`` with the bias gradient computed by msda_colsum_f32."""
+    if (not x.is_cuda) or x.dtype != torch.float32 or linear.bias is None or linear.out_features % 4 or \
+            torch.is_autocast_enabled():
+        return linear(x)
+    return _LinearColsum.apply(x, linear.weight, linear.bias)
+
+
+class _SamplingPrologue(Function):
+    @staticmethod
+    def forward(ctx, query, w_off, b_off, w_attn, b_attn, ref, shapes, n_heads, n_levels, n_points):
+        lib = _cabi.load()
+        q2 = query.reshape(-1, query.shape[-1])
+        rows = q2.shape[0]
+        weight = torch.cat((w_off, w_attn), 0)                    # [M*LP*3, C]: offsets first, logits last
+        bias = torch.cat((b_off, b_attn), 0)
+        proj = torch.addmm(bias, q2, weight.t())                   # one GEMM instead of two (ms_deform_attn.py:99-100)
+        ref_c = _f32c(ref).reshape(rows, n_levels, ref.shape[-1])
+        loc = torch.empty((rows, n_heads, n_levels, n_points, 2), dtype=torch.float32, device=query.device)
+        attn = torch.empty((rows, n_heads, n_levels, n_points), dtype=torch.float32, device=query.device)
+        with torch.cuda.device(query.device):
+            _cabi.check(lib.msda_prologue_forward_f32(proj.data_ptr(), ref_c.data_ptr(), shapes.data_ptr(), rows, n_heads,
+                                                      n_levels, n_points, ref.shape[-1], loc.data_ptr(), attn.data_ptr(),
+                                                      _stream()), "msda_prologue_forward_f32")
+        ctx.save_for_backward(q2, weight, attn, ref_c, shapes)
+        ctx.dims = (n_heads, n_levels, n_points, ref.shape[-1], w_off.shape[0], query.shape)
+        lead = query.shape[:-1]
+        return loc.view(*lead, n_heads, n_levels, n_points, 2), attn.view(*lead, n_heads, n_levels, n_points)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_loc, g_attn):
+        lib = _cabi.load()
+        q2, weight, attn, ref_c, shapes = ctx.saved_tensors
+        m, l, p, rd, n_off, qshape = ctx.dims
+        rows = q2.shape[0]
+        g_proj = torch.empty((rows, weight.shape[0]), dtype=torch.float32, device=q2.device)
+        g_loc, g_attn = _f32c(g_loc), _f32c(g_attn)
+        with torch.cuda.device(q2.device):
+            _cabi.check(lib.msda_prologue_backward_f32(g_loc.data_ptr(), g_attn.data_ptr(), attn.data_ptr(), ref_c.data_ptr(),
+                                                       shapes.data_ptr(), rows, m, l, p, rd, g_proj.data_ptr(), _stream()),
+                        "msda_prologue_backward_f32")
+        gq = torch.mm(g_proj, weight).view(qshape) if ctx.needs_input_grad[0] else None
+        gw = torch.mm(g_proj.t(), q2)
+        gb = colsum(g_proj)
+        return gq, gw[:n_off], gb[:n_off], gw[n_off:], gb[n_off:], None, None, None, None, None
+
+
+def sampling_prologue(query, sampling_offsets: torch.nn.Linear, attention_weights: torch.nn.Linear, reference_points,
+                      spatial_shapes, n_heads, n_levels, n_points):
+    """-> (sampling_locations [.., M, L, P, 2], attention_weights [.., M, L, P]); reference points are constants."""
+    return _SamplingPrologue.apply(query, sampling_offsets.weight, sampling_offsets.bias, attention_weights.weight,
+                                   attention_weights.bias, reference_points, spatial_shapes, n_heads, n_levels, n_points)
+
+
+class _AddLayerNorm(Function):
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps):
+        lib = _cabi.load()
+        cols = a.shape[-1]
+        a2 = a.reshape(-1, cols).contiguous()
+        b2 = b.reshape(-1, cols).contiguous() if b is not None else None
+        rows = a2.shape[0]
+        y = torch.empty_like(a2)
+        z = torch.empty_like(a2) if b2 is not None else a2
+        mean = torch.empty(rows, dtype=torch.float32, device=a.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _cabi.check(lib.msda_add_layernorm_forward_f32(a2.data_ptr(), b2.data_ptr() if b2 is not None else None,
+                                                           gamma.data_ptr(), beta.data_ptr(), rows, cols, float(eps),
+                                                           z.data_ptr() if b2 is not None else None, y.data_ptr(),
+                                                           mean.data_ptr(), rstd.data_ptr(), _stream()),
+                        "msda_add_layernorm_forward_f32")
+        ctx.save_for_backward(z, gamma, mean, rstd)
+        ctx.has_b = b is not None
+        return y.view(a.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _cabi.load()
+        z, gamma, mean, rstd = ctx.saved_tensors
+        rows, cols = z.shape
+        gy2 = gy.reshape(rows, cols).contiguous()
+        dz = torch.empty_like(z)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        with torch.cuda.device(z.device):
+            _cabi.check(lib.msda_layernorm_backward_f32(gy2.data_ptr(), z.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+                                                        rstd.data_ptr(), rows, cols, dz.data_ptr(), dgamma.data_ptr(),
+                                                        dbeta.data_ptr(), _stream()), "msda_layernorm_backward_f32")
+        dz = dz.view(gy.shape)
+        return dz, (dz if ctx.has_b else None), dgamma, dbeta, None
+
+
+def add_layer_norm(a, b, norm: torch.nn.LayerNorm):
+    """``norm(a + b)`` (b may be None) as one forward and one backward kernel."""
+    cols = a.shape[-1]
+    ok = a.is_cuda and a.dtype == torch.float32 and cols in (128, 256, 384, 512) and norm.elementwise_affine and \
+        norm.bias is not None and not torch.is_autocast_enabled() and (b is None or b.dtype == torch.float32)
+    if not ok:
+        return norm(a if b is None else a + b)
+    return _AddLayerNorm.apply(a, b, norm.weight, norm.bias, norm.eps)

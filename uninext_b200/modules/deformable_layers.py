@@ -9,6 +9,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from uninext_b200.functions.fused import add_layer_norm, linear_colsum
+
 from .ms_deform_attn import MSDeformAttn
 
 
@@ -27,9 +29,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         att = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        src = self.norm1(src + self.dropout1(att))
-        ffn = self.linear2(self.dropout2(torch.relu(self.linear1(src))))
-        return self.norm2(src + self.dropout3(ffn))
+        src = add_layer_norm(src, self.dropout1(att), self.norm1)
+        ffn = linear_colsum(self.dropout2(torch.relu(linear_colsum(src, self.linear1))), self.linear2)
+        return add_layer_norm(src, self.dropout3(ffn), self.norm2)
 
 
 class DeformableTransformerDecoderLayer(nn.Module):
@@ -47,12 +49,12 @@ class DeformableTransformerDecoderLayer(nn.Module):
                 src_padding_mask=None):
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
         sa = self.self_attn(qk, qk, tgt.transpose(0, 1))[0].transpose(0, 1)
-        tgt = self.norm2(tgt + self.dropout2(sa))
+        tgt = add_layer_norm(tgt, self.dropout2(sa), self.norm2)
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes, level_start_index,
                              src_padding_mask)
-        tgt = self.norm1(tgt + self.dropout1(ca))
-        ffn = self.linear2(self.dropout3(torch.relu(self.linear1(tgt))))
-        return self.norm3(tgt + self.dropout4(ffn))
+        tgt = add_layer_norm(tgt, self.dropout1(ca), self.norm1)
+        ffn = linear_colsum(self.dropout3(torch.relu(linear_colsum(tgt, self.linear1))), self.linear2)
+        return add_layer_norm(tgt, self.dropout4(ffn), self.norm3)
 
 
 def encoder_reference_points(spatial_shapes_list, valid_ratios, device):
@@ -83,7 +85,11 @@ class DeformableStack(nn.Module):
         self.decoder = nn.ModuleList(DeformableTransformerDecoderLayer(**kw) for _ in range(num_layers))
         self.level_embed = nn.Parameter(torch.randn(n_levels, d_model) * 0.02)
         self.query_embed = nn.Embedding(num_queries, d_model * 2)
-        self.reference_boxes = nn.Linear(d_model, 4)
+        # decoder reference boxes (cx, cy, w, h): constants here, as with the reference's box refinement, which feeds each
+        # layer detached boxes (deformable_transformer.py: `reference_points = new_reference_points.detach()`)
+        g = torch.Generator().manual_seed(0)
+        boxes = torch.cat((torch.rand(num_queries, 2, generator=g), 0.05 + 0.35 * torch.rand(num_queries, 2, generator=g)), -1)
+        self.register_buffer("reference_boxes", boxes)
         self.n_levels = n_levels
 
     def forward(self, src, pos, spatial_shapes_list, spatial_shapes, level_start_index):
@@ -100,7 +106,7 @@ class DeformableStack(nn.Module):
             memory = layer(memory, pos, ref, spatial_shapes, level_start_index, None)
         qpos, tgt = self.query_embed.weight.chunk(2, dim=-1)
         qpos, tgt = qpos[None].expand(n, -1, -1), tgt[None].expand(n, -1, -1)
-        boxes = self.reference_boxes(qpos).sigmoid()                                     # [N, Q, 4] (cx, cy, w, h)
+        boxes = self.reference_boxes[None].expand(n, -1, -1)                              # [N, Q, 4] (cx, cy, w, h)
         ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
         out = tgt
         for layer in self.decoder:

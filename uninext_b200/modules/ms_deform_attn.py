@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from uninext_b200.functions import MSDeformAttnFunction, MSDeformAttnFunctionBF16
+from uninext_b200.functions.fused import linear_colsum, sampling_prologue
 
 
 def _power_of_two(n: int) -> bool:
@@ -26,7 +27,7 @@ def _power_of_two(n: int) -> bool:
 
 
 class MSDeformAttn(nn.Module):
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None, fused=True):
         super().__init__()
         if d_model % n_heads:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
@@ -36,6 +37,7 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64                     # accepted for drop-in compatibility (ms_deform_attn.py:48)
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.op_dtype = op_dtype
+        self.fused = fused           # one-pass prologue / bias-gradient kernels around the cuBLAS GEMMs (same maths)
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
         self.value_proj = nn.Linear(d_model, d_model)
@@ -75,20 +77,26 @@ class MSDeformAttn(nn.Module):
         n, lq, _ = query.shape
         s = input_flatten.shape[1]
         m, l, p = self.n_heads, self.n_levels, self.n_points
-        value = self.value_proj(input_flatten)
+        fused = (self.fused and query.is_cuda and query.dtype == torch.float32 and l * p <= 32
+                 and not reference_points.requires_grad)
+        value = linear_colsum(input_flatten, self.value_proj) if fused else self.value_proj(input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(n, s, m, self.d_model // m)
-        offsets = self.sampling_offsets(query).view(n, lq, m, l, p, 2)
-        weights = F.softmax(self.attention_weights(query).view(n, lq, m, l * p), dim=-1).view(n, lq, m, l, p)
-        loc = self.sampling_locations(offsets, reference_points, input_spatial_shapes)
+        if fused:
+            loc, weights = sampling_prologue(query, self.sampling_offsets, self.attention_weights, reference_points,
+                                             input_spatial_shapes, m, l, p)
+        else:
+            offsets = self.sampling_offsets(query).view(n, lq, m, l, p, 2)
+            weights = F.softmax(self.attention_weights(query).view(n, lq, m, l * p), dim=-1).view(n, lq, m, l, p)
+            loc = self.sampling_locations(offsets, reference_points, input_spatial_shapes)
         if self.op_dtype == torch.bfloat16:
             out = MSDeformAttnFunctionBF16.apply(value, input_spatial_shapes, input_level_start_index, loc, weights,
                                                  self.im2col_step).to(query.dtype)
         else:
             out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
                                              weights.contiguous(), self.im2col_step)
-        return self.output_proj(out)
+        return linear_colsum(out, self.output_proj) if fused else self.output_proj(out)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
