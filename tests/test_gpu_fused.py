@@ -102,6 +102,22 @@ def test_linear_colsum_matches_linear():
     assert _rel(got[1], x.grad) < 1e-3 and _rel(got[2], lin.weight.grad) < 1e-3 and _rel(got[3], lin.bias.grad) < 1e-4
 
 
+def test_linear_relu_and_split_k_weight_grad():
+    from uninext_b200.functions.fused import weight_grad
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(256, 512).to(DEV)
+    x = torch.randn(2, 9000, 256, device=DEV, requires_grad=True)          # 18000 rows -> split-K path (256*512 outputs)
+    gy = torch.randn(2, 9000, 512, device=DEV)
+    y = linear_colsum(x, lin, relu=True); y.backward(gy)
+    got = (y.detach(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None; lin.weight.grad = None; lin.bias.grad = None
+    y2 = torch.relu(lin(x)); y2.backward(gy)
+    assert torch.allclose(got[0], y2, rtol=1e-4, atol=1e-4)
+    assert _rel(got[1], x.grad) < 1e-3 and _rel(got[2], lin.weight.grad) < 1e-3 and _rel(got[3], lin.bias.grad) < 1e-4
+    g2, x2 = torch.randn(44646, 384, device=DEV), torch.randn(44646, 256, device=DEV)
+    assert _rel(weight_grad(g2, x2), g2.double().t() @ x2.double()) < 1e-4
+
+
 def test_fused_and_unfused_module_agree():
     from uninext_b200.workloads import CONFIGS, level_tensors
     from uninext_b200.modules.deformable_layers import encoder_reference_points

@@ -37,32 +37,57 @@ def colsum(x2d: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def weight_grad(g2: torch.Tensor, x2: torch.Tensor, splits: int = 16) -> torch.Tensor:
+    """g2^T @ x2 for a tall-skinny problem ([rows, n]^T @ [rows, c], rows >> n, c).  cuBLAS picks a 16-CTA kernel for the
+    un-split product when n*c is small; splitting the reduction into a strided-batched GEMM + a tiny sum fills the GPU."""
+    rows, n = g2.shape
+    c = x2.shape[1]
+    if rows < 8192 or n * c > 256 * 512:
+        return torch.mm(g2.t(), x2)
+    ch = rows // splits
+    kp = ch * splits
+    gw = torch.bmm(g2[:kp].view(splits, ch, n).transpose(1, 2), x2[:kp].view(splits, ch, c)).sum(0)
+    if kp < rows:
+        gw = gw.addmm_(g2[kp:].t(), x2[kp:])
+    return gw
+
+
 class _LinearColsum(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, relu):
         x2 = x.reshape(-1, x.shape[-1])
-        ctx.save_for_backward(x2, weight)
-        ctx.xshape = x.shape
-        y = torch.addmm(bias, x2, weight.t())
+        if relu:                                             # bias + ReLU in the cuBLASLt epilogue
+            y = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
+            ctx.save_for_backward(x2, weight, y)
+        else:
+            y = torch.addmm(bias, x2, weight.t())
+            ctx.save_for_backward(x2, weight)
+        ctx.xshape, ctx.relu = x.shape, relu
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x2, weight = ctx.saved_tensors
-        g2 = g.reshape(-1, g.shape[-1]).contiguous()
+        x2, weight = ctx.saved_tensors[:2]
+        g2 = g.reshape(-1, g.shape[-1])
+        if ctx.relu:
+            g2 = torch.ops.aten.threshold_backward(g2, ctx.saved_tensors[2], 0.0)
+        else:
+            g2 = g2.contiguous()
         gx = torch.mm(g2, weight).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        gw = torch.mm(g2.t(), x2) if ctx.needs_input_grad[1] else None
+        gw = weight_grad(g2, x2) if ctx.needs_input_grad[1] else None
         gb = colsum(g2) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
-def linear_colsum(x, linear: torch.nn.Linear):
-    """``linear(x)`` with the bias gradient computed by msda_colsum_f32."""
+def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False):
+    """``linear(x)`` (optionally followed by ReLU) with the bias gradient computed by msda_colsum_f32 and the weight
+    gradient as a split-K batched GEMM."""
     if (not x.is_cuda) or x.dtype != torch.float32 or linear.bias is None or linear.out_features % 4 or \
             torch.is_autocast_enabled():
-        return linear(x)
-    return _LinearColsum.apply(x, linear.weight, linear.bias)
+        y = linear(x)
+        return torch.relu(y) if relu else y
+    return _LinearColsum.apply(x, linear.weight, linear.bias, relu)
 
 
 class _SamplingPrologue(Function):
@@ -100,7 +125,7 @@ class _SamplingPrologue(Function):
                                                        shapes.data_ptr(), rows, m, l, p, rd, g_proj.data_ptr(), _stream()),
                         "msda_prologue_backward_f32")
         gq = torch.mm(g_proj, weight).view(qshape) if ctx.needs_input_grad[0] else None
-        gw = torch.mm(g_proj.t(), q2)
+        gw = weight_grad(g_proj, q2)
         gb = colsum(g_proj)
         return gq, gw[:n_off], gb[:n_off], gw[n_off:], gb[n_off:], None, None, None, None, None
 

@@ -30,7 +30,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         att = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
         src = add_layer_norm(src, self.dropout1(att), self.norm1)
-        ffn = linear_colsum(self.dropout2(torch.relu(linear_colsum(src, self.linear1))), self.linear2)
+        ffn = linear_colsum(self.dropout2(linear_colsum(src, self.linear1, relu=True)), self.linear2)
         return add_layer_norm(src, self.dropout3(ffn), self.norm2)
 
 
@@ -53,7 +53,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes, level_start_index,
                              src_padding_mask)
         tgt = add_layer_norm(tgt, self.dropout1(ca), self.norm1)
-        ffn = linear_colsum(self.dropout3(torch.relu(linear_colsum(tgt, self.linear1))), self.linear2)
+        ffn = linear_colsum(self.dropout3(linear_colsum(tgt, self.linear1, relu=True)), self.linear2)
         return add_layer_norm(tgt, self.dropout4(ffn), self.norm3)
 
 
@@ -98,9 +98,8 @@ class DeformableStack(nn.Module):
         valid = torch.ones(n, self.n_levels, 2, device=src.device)
         ref = encoder_reference_points(spatial_shapes_list, valid, src.device)
         # per-level embedding added to the position encoding (deformable_transformer.py:193-195 lvl_pos_embed)
-        lvl = torch.cat([torch.full((h * w,), i, device=src.device, dtype=torch.long)
-                         for i, (h, w) in enumerate(spatial_shapes_list)])
-        pos = pos + self.level_embed[lvl][None]
+        pos = pos + torch.cat([self.level_embed[i].view(1, 1, -1).expand(1, h * w, -1)
+                               for i, (h, w) in enumerate(spatial_shapes_list)], 1)
         memory = src
         for layer in self.encoder:
             memory = layer(memory, pos, ref, spatial_shapes, level_start_index, None)
