@@ -117,6 +117,12 @@ int msda_layernorm_backward_f32(const float *dy, const float *z, const float *ga
                                 const float *rstd, int64_t rows, int cols, float *dz, float *dgamma, float *dbeta,
                                 void *stream);
 
+/* ---- tcgen05 GEMM for the Linears that bracket the op:  C[M,N] = A[M,K] . W[N,K]^T + bias[N]  (fp32 storage, TF32 MMA
+ * with fp32 accumulation in tensor memory; TMA-fed).  K % 32 == 0, N % 32 == 0 (N % 64 == 0 above 256), N <= 512.
+ * Replaces torch.nn.functional.linear for value_proj / output_proj / the concatenated sampling projection
+ * (ops/modules/ms_deform_attn.py:95,99-100,115) when TF32 GEMMs are allowed. bias may be NULL. */
+int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t M, int N, int K, float *C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

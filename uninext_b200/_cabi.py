@@ -32,6 +32,7 @@ SIGNATURES = {
     "msda_colsum_f32": (_i, [_vp, ctypes.c_int64, _i, _vp, _vp]),
     "msda_add_layernorm_forward_f32": (_i, [_vp] * 4 + [ctypes.c_int64, _i, ctypes.c_float] + [_vp] * 5),
     "msda_layernorm_backward_f32": (_i, [_vp] * 5 + [ctypes.c_int64, _i] + [_vp] * 4),
+    "msda_linear_tf32": (_i, [_vp] * 3 + [ctypes.c_int64, _i, _i, _vp, _vp]),
 }
 ABI_VERSION = 1
 

@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmsda_b200.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
-SOURCES = ["msda_cabi.cu"]
+SOURCES = ["msda_cabi.cu", "msda_gemm_sm100.cu"]
 HEADERS = ["msda_common.cuh", "msda_tiled.cuh", "msda_generic.cuh", "msda_module.cuh"]
 
 NVCC_FLAGS = [

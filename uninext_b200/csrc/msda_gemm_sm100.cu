@@ -1,0 +1,317 @@
+// msda_gemm_sm100.cu -- hand-written tcgen05 GEMM for the Linears that bracket the op (north_star: "tensor cores only
+// on the fused value_proj / output_proj GEMMs"):      C[M, N] = A[M, K] . W[N, K]^T + bias[N]        (fp32 in/out, TF32 MMA)
+//
+// Shape regime: M = N_batch * S tokens (tens of thousands), K = d_model (256), N in {256, 384}.  Memory-bound: A is read
+// once, C written once, W (<= 384 KB) is re-read by every CTA from L2.
+//
+// Structure (one CTA = one 128-row tile of C, all N columns):
+//   warp 0   : TMA producer -- cp.async.bulk.tensor 2D loads of A[128 x 32] and W[N x 32] (128-byte rows, SWIZZLE_128B)
+//              into a ring of shared-memory stages, completion on mbarriers.
+//   warp 1   : TMEM allocation + MMA issue -- one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N<=256,
+//              K=8 per instruction, 4 per 32-wide k-block), accumulating in TMEM; tcgen05.commit releases stages.
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns at a time, + bias, 16-byte global stores (one row per thread).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/msda_b200.h"
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                   // tf32: 32 bytes per instruction
+constexpr int kThreads = 192;
+constexpr int kMaxN = 512;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+                 "[%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
+// leading byte offset [16,30) (unused for swizzled K-major: 1), stride byte offset [32,46) = 1024 B between 8-row groups,
+// version = 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc(const void *smem, unsigned k_byte_offset) {
+    const uint64_t addr = (smem_u32(smem) + k_byte_offset) >> 4;
+    return (addr & 0x3fffull) | (1ull << 16) | ((1024ull >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10)/[10,13), both
+// K-major, n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((unsigned)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` (both CTAs of the pair share each W stage)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Params {
+    long long M;
+    int N, K, stages, tmem_cols, w_box_rows, acc_bufs;      // acc_bufs = 2 when two accumulators fit in TMEM (N <= 256)
+    const float *bias;
+    float *C;
+};
+
+// Persistent: cluster c (a CTA pair) handles row-tile pairs c, c+G/2, ...; CTA `rank` of the pair owns tile 2*pair+rank.
+// Three pipelines: smem stages (TMA <-> MMA, full/empty), TMEM accumulators (MMA <-> epilogue, tmem_full/tmem_empty,
+// double-buffered when N <= 256), and the tile loop itself.  The pair shares W: each CTA loads half of W's rows per
+// k-block and TMA-multicasts it into both CTAs' stage (halves the L2 -> SM traffic of the operand every tile re-reads);
+// a stage is refilled only after BOTH CTAs' MMAs have consumed it (empty barriers count 2, signalled by multicast commits).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+linear_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms (8 rows x 128 B) must start 1024-byte aligned
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N, KB = p.K / BLOCK_K;
+    const unsigned a_bytes = BLOCK_M * BLOCK_K * 4, w_bytes = (unsigned)N * BLOCK_K * 4, stage_bytes = a_bytes + w_bytes;
+    const long long ntiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const long long npairs = (ntiles + 1) / 2;
+    const unsigned rank = cluster_ctarank();
+    const long long pair0 = blockIdx.x / 2, pair_stride = gridDim.x / 2;
+    // per epilogue warp: 32x33 fp32 transpose tile, placed after the stage ring
+    float (*xpose)[32][33] = reinterpret_cast<float (*)[32][33]>(smem + (size_t)p.stages * stage_bytes);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                       // one warp allocates TMEM (power-of-two columns) and later frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((unsigned)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                    // the peer's barriers exist before anything is multicast into this CTA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            unsigned it = 0;                                             // global k-block counter across tiles
+            const int half = N / 2;                                      // rows of W this CTA loads and multicasts
+            for (long long pr = pair0; pr < npairs; pr += pair_stride) {
+                const int row0 = (int)((pr * 2 + rank) * BLOCK_M);       // may lie beyond M for the last pair: TMA zero-fills
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);                    // both CTAs have drained this stage
+                    unsigned char *sa = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], stage_bytes);           // own A tile + both halves of W
+                    tma_load_2d(sa, &map_a, kb * BLOCK_K, row0, &full_bar[s]);
+                    tma_load_2d_mc(sa + a_bytes + (size_t)rank * half * BLOCK_K * 4, &map_w, kb * BLOCK_K, (int)rank * half,
+                                   &full_bar[s], (uint16_t)3);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        unsigned it = 0, t = 0;
+        for (long long pr = pair0; pr < npairs; pr += pair_stride, ++t) {
+            const unsigned buf = t % p.acc_bufs, use = t / p.acc_bufs;
+            mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);              // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_base + buf * (uint32_t)N;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const unsigned char *sa = smem + (size_t)s * stage_bytes;
+                    const unsigned char *sw = sa + a_bytes;
+                    for (int n0 = 0; n0 < N; n0 += 256) {
+                        const int nt = min(256, N - n0);
+                        const uint32_t idesc = umma_idesc_tf32(BLOCK_M, nt);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_tf32(acc + (uint32_t)n0, umma_desc(sa, k * UMMA_K * 4),
+                                      umma_desc(sw + (size_t)n0 * BLOCK_K * 4, k * UMMA_K * 4), idesc, (kb | k) != 0);
+                    }
+                    umma_commit_mc(&empty_bar[s], (uint16_t)3);          // tell both producers this CTA is done with the stage
+                    if (kb == KB - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> smem transpose -> (+bias) -> coalesced global stores =====
+        const int ew = warp - 2;
+        const int lane_base = (warp & 3) * 32;                          // a warp may touch TMEM lanes 32*(warp%4) .. +31
+        float (*xp)[33] = xpose[ew];
+        unsigned t = 0;
+        for (long long pr = pair0; pr < npairs; pr += pair_stride, ++t) {
+            const unsigned buf = t % p.acc_bufs, use = t / p.acc_bufs;
+            mbar_wait(&tmem_full_bar[buf], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long rbase = (pr * 2 + rank) * BLOCK_M + lane_base;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)N + (uint32_t)c0, v);
+                const float bia = p.bias != nullptr ? __ldg(p.bias + c0 + lane) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xp[lane][i] = v[i];        // lane = row; conflict-free with the 33 pad
+                __syncwarp();
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r)                             // lane = column: 128 contiguous bytes per row
+                    if (rbase + r < p.M) p.C[(rbase + r) * (long long)N + c0 + lane] = xp[r][lane] + bia;
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                    // neither CTA leaves while the peer may still multicast into it
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols) : "memory");
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+bool make_map(CUtensorMap *map, const float *base, long long rows, int K, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace gemm
+
+extern std::atomic<uint64_t> g_msda_gemm_launches;
+std::atomic<uint64_t> g_msda_gemm_launches{0};
+
+extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t M, int N, int K, float *C,
+                                void *stream) {
+    using namespace gemm;
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || K % BLOCK_K || N % 32 || N > kMaxN) return MSDA_E_BADARG;   // epilogue reads 32 TMEM columns at a time
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15u) return MSDA_E_BADARG;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return MSDA_E_BADARG;
+    if (N > 256 && (N % 64)) return MSDA_E_BADARG;      // MMA N tiles are multiples of 16, W halves whole swizzle atoms
+    const int w_box_rows = N / 2;                       // each CTA of the pair loads (and multicasts) half of W
+    CUtensorMap map_a, map_w;
+    if (!make_map(&map_a, A, M, K, BLOCK_M) || !make_map(&map_w, W, N, K, w_box_rows)) return MSDA_E_NODEVICE;
+    Params p;
+    p.w_box_rows = w_box_rows;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.C = C;
+    const unsigned stage_bytes = (BLOCK_M + N) * BLOCK_K * 4;
+    constexpr unsigned kXposeBytes = 4 * 32 * 33 * 4, kDynMax = 232448 - 1024;      // 227 KB minus the static part
+    int stages = (int)((kDynMax - 1024u - kXposeBytes) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages > K / BLOCK_K) stages = K / BLOCK_K;
+    if (stages < 1) return MSDA_E_BADARG;
+    p.stages = stages;
+    p.acc_bufs = (N <= 256) ? 2 : 1;
+    const int need = N * p.acc_bufs;
+    p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + kXposeBytes;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const long long tiles = (M + BLOCK_M - 1) / BLOCK_M, pairs = (tiles + 1) / 2;
+    const long long max_clusters = sms / 2;
+    const unsigned grid = 2u * (unsigned)(pairs < max_clusters ? pairs : max_clusters);
+    linear_tf32_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_a, map_w, p);
+    g_msda_gemm_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}

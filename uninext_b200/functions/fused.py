@@ -52,15 +52,41 @@ def weight_grad(g2: torch.Tensor, x2: torch.Tensor, splits: int = 16) -> torch.T
     return gw
 
 
+def tcgen05_linear_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
+    """msda_linear_tf32 constraints (include/msda_b200.h): fp32, K % 32 == 0, N % 32 == 0 (N % 64 == 0 above 256), N <= 512."""
+    n, k = weight.shape
+    return (x2.is_cuda and x2.dtype == torch.float32 and weight.dtype == torch.float32 and k % 32 == 0 and n % 32 == 0
+            and n <= 512 and (n <= 256 or n % 64 == 0) and x2.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
+
+
+def tcgen05_linear(x2: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    """x2 @ weight.T + bias on the hand-written tcgen05 kernel (TF32 MMA, fp32 accumulate in tensor memory)."""
+    x2, weight = x2.contiguous(), weight.contiguous()
+    m, k = x2.shape
+    n = weight.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        _cabi.check(_cabi.load().msda_linear_tf32(x2.data_ptr(), weight.data_ptr(),
+                                                  bias.data_ptr() if bias is not None else None, m, n, k, out.data_ptr(),
+                                                  _stream()), "msda_linear_tf32")
+    return out
+
+
+def _gemm_bias(x2, weight, bias, gemm):
+    if gemm == "tcgen05" and tcgen05_linear_ok(x2, weight):
+        return tcgen05_linear(x2, weight, bias)
+    return torch.addmm(bias, x2, weight.t())
+
+
 class _LinearColsum(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, relu):
+    def forward(ctx, x, weight, bias, relu, gemm):
         x2 = x.reshape(-1, x.shape[-1])
         if relu:                                             # bias + ReLU in the cuBLASLt epilogue
             y = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
             ctx.save_for_backward(x2, weight, y)
         else:
-            y = torch.addmm(bias, x2, weight.t())
+            y = _gemm_bias(x2, weight, bias, gemm)
             ctx.save_for_backward(x2, weight)
         ctx.xshape, ctx.relu = x.shape, relu
         return y.view(*x.shape[:-1], weight.shape[0])
@@ -77,28 +103,28 @@ class _LinearColsum(Function):
         gx = torch.mm(g2, weight).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         gw = weight_grad(g2, x2) if ctx.needs_input_grad[1] else None
         gb = colsum(g2) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False):
+def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False, gemm: str = "cublas"):
     """``linear(x)`` (optionally followed by ReLU) with the bias gradient computed by msda_colsum_f32 and the weight
-    gradient as a split-K batched GEMM."""
+    gradient as a split-K batched GEMM.  ``gemm="tcgen05"`` runs the forward product on msda_linear_tf32."""
     if (not x.is_cuda) or x.dtype != torch.float32 or linear.bias is None or linear.out_features % 4 or \
             torch.is_autocast_enabled():
         y = linear(x)
         return torch.relu(y) if relu else y
-    return _LinearColsum.apply(x, linear.weight, linear.bias, relu)
+    return _LinearColsum.apply(x, linear.weight, linear.bias, relu, gemm)
 
 
 class _SamplingPrologue(Function):
     @staticmethod
-    def forward(ctx, query, w_off, b_off, w_attn, b_attn, ref, shapes, n_heads, n_levels, n_points):
+    def forward(ctx, query, w_off, b_off, w_attn, b_attn, ref, shapes, n_heads, n_levels, n_points, gemm):
         lib = _cabi.load()
         q2 = query.reshape(-1, query.shape[-1])
         rows = q2.shape[0]
         weight = torch.cat((w_off, w_attn), 0)                    # [M*LP*3, C]: offsets first, logits last
         bias = torch.cat((b_off, b_attn), 0)
-        proj = torch.addmm(bias, q2, weight.t())                   # one GEMM instead of two (ms_deform_attn.py:99-100)
+        proj = _gemm_bias(q2, weight, bias, gemm)                  # one GEMM instead of two (ms_deform_attn.py:99-100)
         ref_c = _f32c(ref).reshape(rows, n_levels, ref.shape[-1])
         loc = torch.empty((rows, n_heads, n_levels, n_points, 2), dtype=torch.float32, device=query.device)
         attn = torch.empty((rows, n_heads, n_levels, n_points), dtype=torch.float32, device=query.device)
@@ -127,14 +153,15 @@ class _SamplingPrologue(Function):
         gq = torch.mm(g_proj, weight).view(qshape) if ctx.needs_input_grad[0] else None
         gw = weight_grad(g_proj, q2)
         gb = colsum(g_proj)
-        return gq, gw[:n_off], gb[:n_off], gw[n_off:], gb[n_off:], None, None, None, None, None
+        return gq, gw[:n_off], gb[:n_off], gw[n_off:], gb[n_off:], None, None, None, None, None, None
 
 
 def sampling_prologue(query, sampling_offsets: torch.nn.Linear, attention_weights: torch.nn.Linear, reference_points,
-                      spatial_shapes, n_heads, n_levels, n_points):
+                      spatial_shapes, n_heads, n_levels, n_points, gemm: str = "cublas"):
     """-> (sampling_locations [.., M, L, P, 2], attention_weights [.., M, L, P]); reference points are constants."""
     return _SamplingPrologue.apply(query, sampling_offsets.weight, sampling_offsets.bias, attention_weights.weight,
-                                   attention_weights.bias, reference_points, spatial_shapes, n_heads, n_levels, n_points)
+                                   attention_weights.bias, reference_points, spatial_shapes, n_heads, n_levels, n_points,
+                                   gemm)
 
 
 class _AddLayerNorm(Function):

@@ -27,7 +27,7 @@ def _power_of_two(n: int) -> bool:
 
 
 class MSDeformAttn(nn.Module):
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None, fused=True):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None, fused=True, gemm="cublas"):
         super().__init__()
         if d_model % n_heads:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
@@ -37,7 +37,10 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64                     # accepted for drop-in compatibility (ms_deform_attn.py:48)
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.op_dtype = op_dtype
-        self.fused = fused           # one-pass prologue / bias-gradient kernels around the cuBLAS GEMMs (same maths)
+        self.fused = fused           # one-pass prologue / bias-gradient kernels around the GEMMs (same maths)
+        # "cublas" (default: measured faster) or "tcgen05": forward products of value_proj / output_proj / the sampling
+        # projection on the hand-written TF32 tensor-core kernel msda_linear_tf32 (TF32 rounding, like allow_tf32)
+        self.gemm = gemm
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
         self.value_proj = nn.Linear(d_model, d_model)
@@ -79,13 +82,13 @@ class MSDeformAttn(nn.Module):
         m, l, p = self.n_heads, self.n_levels, self.n_points
         fused = (self.fused and query.is_cuda and query.dtype == torch.float32 and l * p <= 32
                  and not reference_points.requires_grad)
-        value = linear_colsum(input_flatten, self.value_proj) if fused else self.value_proj(input_flatten)
+        value = linear_colsum(input_flatten, self.value_proj, gemm=self.gemm) if fused else self.value_proj(input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(n, s, m, self.d_model // m)
         if fused:
             loc, weights = sampling_prologue(query, self.sampling_offsets, self.attention_weights, reference_points,
-                                             input_spatial_shapes, m, l, p)
+                                             input_spatial_shapes, m, l, p, gemm=self.gemm)
         else:
             offsets = self.sampling_offsets(query).view(n, lq, m, l, p, 2)
             weights = F.softmax(self.attention_weights(query).view(n, lq, m, l * p), dim=-1).view(n, lq, m, l, p)
@@ -96,7 +99,7 @@ class MSDeformAttn(nn.Module):
         else:
             out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, loc.contiguous(),
                                              weights.contiguous(), self.im2col_step)
-        return linear_colsum(out, self.output_proj) if fused else self.output_proj(out)
+        return linear_colsum(out, self.output_proj, gemm=self.gemm) if fused else self.output_proj(out)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
