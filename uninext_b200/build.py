@@ -29,8 +29,6 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
 ]
-if os.environ.get("MSDA_EXPERIMENTS") == "1":      # extra kernel instantiations selectable by env (A/B runs only)
-    NVCC_FLAGS.append("-DMSDA_EXPERIMENTS")
 
 
 def nvcc_path() -> str:

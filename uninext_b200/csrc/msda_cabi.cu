@@ -81,10 +81,6 @@ bool use_tma_staging(const Dims &d) {
 
 constexpr int kFwdMinCtas = 4, kBwdMinCtas = 2;     // r01d sweep: fwd flat for 3..5, bwd best at 2 (128 regs, no spills)
 
-int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return (e && e[0]) ? atoi(e) : dflt;
-}
 
 template <typename T> struct FwdVec { static constexpr int v = 16 / sizeof(T); };      // 16-byte row slices
 template <typename T> struct BwdVec { static constexpr int v = 4; };                  // 4 channels per lane (see RowVec)
