@@ -79,6 +79,17 @@ bool use_tma_staging(const Dims &d) {
     return !off && !allow_patches() && ((d.L * d.P) % 4 == 0);
 }
 
+// Small launches (decoder-style calls: a few thousand pairs) cannot hide the row-load latency with other warps; there the
+// taps of each pair are split over the groups of a warp (template SPLIT).  MSDA_SPLIT=0/1 forces the choice (A/B).
+bool use_split(unsigned npairs) {
+    static int force = -2;
+    if (force == -2) { const char *e = getenv("MSDA_SPLIT"); force = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }
+    if (force >= 0) return force == 1;
+    // measured (gpurun r01p): 4 800 pairs (cfg2 decoder call) fwd 18.4 -> 14.4 us, bwd 29.7 -> 27.6 us; neutral-to-worse
+    // from 14 400 pairs up, so only launches with fewer than ~56 pairs per SM are split
+    return npairs <= (unsigned)num_sms() * 56u;
+}
+
 constexpr int kFwdMinCtas = 4, kBwdMinCtas = 2;     // r01d sweep: fwd flat for 3..5, bwd best at 2 (128 regs, no spills)
 
 
@@ -89,16 +100,21 @@ template <typename T, int D, int LP_MAX>
 cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                        const Dims &d, T *out, cudaStream_t st) {
     constexpr int VEC = FwdVec<T>::v;
+    constexpr int GPW = 32 / (D / VEC);
     constexpr bool kCanStage = (LP_MAX <= 16);          // per-warp double buffer must fit static shared memory
-    const bool tma = kCanStage && use_tma_staging(d);
-    auto kern = tma ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage>
-                    : msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false>;
-    static int slots_tma = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage>);
-    static int slots_ldg = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false>);
-    int slots = tma ? slots_tma : slots_ldg;
+    constexpr bool kCanSplit = (LP_MAX % GPW == 0) && (LP_MAX / GPW <= D / VEC);
     const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
-    constexpr unsigned kIterPairs = msda::kTiledWarps * (32 / (D / VEC));
-    const unsigned tiles_ub = (npairs + kIterPairs - 1) / kIterPairs;        // linear order (patch order has fewer, larger tiles)
+    const bool split = kCanSplit && use_split(npairs);
+    const bool tma = !split && kCanStage && use_tma_staging(d);
+    auto kern = split ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>
+                : tma ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>
+                      : msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>;
+    static int slots_split = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>);
+    static int slots_tma = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>);
+    static int slots_ldg = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>);
+    int slots = split ? slots_split : tma ? slots_tma : slots_ldg;
+    const unsigned iter_pairs = msda::kTiledWarps * (split ? 1 : GPW);
+    const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;        // linear order (patch order has fewer, larger tiles)
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P, npairs,
                                                allow_patches(), out);
@@ -110,16 +126,21 @@ template <typename T, int D, int LP_MAX>
 cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                        const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
     constexpr int VEC = BwdVec<T>::v;
+    constexpr int GPW = 32 / (D / VEC);
     constexpr bool kCanStage = (LP_MAX <= 16);
-    const bool tma = kCanStage && use_tma_staging(d);
-    auto kern = tma ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage>
-                    : msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false>;
-    static int slots_tma = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage>);
-    static int slots_ldg = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false>);
-    int slots = tma ? slots_tma : slots_ldg;
+    constexpr bool kCanSplit = (LP_MAX % GPW == 0) && (LP_MAX / GPW <= D / VEC);
     const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
-    constexpr unsigned kIterPairs = msda::kTiledWarps * (32 / (D / VEC));
-    const unsigned tiles_ub = (npairs + kIterPairs - 1) / kIterPairs;
+    const bool split = kCanSplit && use_split(npairs);
+    const bool tma = !split && kCanStage && use_tma_staging(d);
+    auto kern = split ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, kCanSplit>
+                : tma ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage, false>
+                      : msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, false>;
+    static int slots_split = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, kCanSplit>);
+    static int slots_tma = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage, false>);
+    static int slots_ldg = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, false>);
+    int slots = split ? slots_split : tma ? slots_tma : slots_ldg;
+    const unsigned iter_pairs = msda::kTiledWarps * (split ? 1 : GPW);
+    const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
                                                npairs, allow_patches(), gv, gl, ga);

@@ -93,7 +93,8 @@ __device__ __forceinline__ TileCtx decode_tile(const WorkMap &wm, unsigned tile,
 }
 
 // Which (b, q, m) pair does this group handle in iteration `it` of the tile?  Returns false for idle slots.
-template <int GPW>
+// PPW = pairs per warp: GPW (one pair per group) or 1 (SPLIT: the groups of a warp share one pair and split its taps).
+template <int GPW, int PPW>
 __device__ __forceinline__ bool slot_pair(const WorkMap &wm, const TileCtx &t, int it, int warp, int grp, int Lq, int M,
                                           unsigned npairs, unsigned &pair, int &b, int &m) {
     if (wm.patches) {
@@ -104,7 +105,7 @@ __device__ __forceinline__ bool slot_pair(const WorkMap &wm, const TileCtx &t, i
         pair = ((unsigned)t.b * (unsigned)Lq + (unsigned)q) * (unsigned)M + (unsigned)t.m;
         return ok;
     }
-    const unsigned p = t.base_pair + (unsigned)(warp * GPW + grp);        // linear tiles are a single iteration
+    const unsigned p = t.base_pair + (unsigned)(warp * PPW + (PPW == 1 ? 0 : grp));     // linear tiles: a single iteration
     const bool ok = p < npairs;
     pair = ok ? p : npairs - 1;
     m = (int)(pair % (unsigned)M);
@@ -178,22 +179,28 @@ __device__ __forceinline__ float4 masked_weights(const TapGeom &g, float a) {
 // ------------------------------------------------------------------------------------------------------------
 // forward:  out[b,q,m,:] = sum_taps a * bilinear(value_l[b,:,m,:], x, y)            (reference cuh:237-299)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA>
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
                int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches, T *__restrict__ out)
 {
     constexpr int LPR = D / VEC;            // lanes per row
-    constexpr int GPW = 32 / LPR;           // (b,q,m) pairs in flight per warp
-    constexpr int NSL = LP_MAX / LPR;       // taps resolved per lane
-    constexpr int ITERS = kTileSlots / (kTiledWarps * GPW);
+    constexpr int GPW = 32 / LPR;           // groups per warp
+    // SPLIT (small problems, e.g. decoder-style calls): the GPW groups of a warp share ONE pair and take LP_MAX/GPW taps
+    // each, so a pair's 4*L*P row loads are spread over the whole warp instead of queuing behind one group -- 4x more
+    // loads in flight per pair when the launch is too small to hide latency with other warps.
+    constexpr int PPW = SPLIT ? 1 : GPW;                    // pairs in flight per warp
+    constexpr int TPG = SPLIT ? LP_MAX / GPW : LPR;         // live tap records per group and round
+    constexpr int NSL = SPLIT ? 1 : LP_MAX / LPR;           // record rounds
+    constexpr int ITERS = SPLIT ? 1 : kTileSlots / (kTiledWarps * GPW);
     static_assert(D % VEC == 0 && (LPR & (LPR - 1)) == 0 && LPR <= 32 && LP_MAX % LPR == 0, "bad tiling");
-    static_assert(kTileSlots % (kTiledWarps * GPW) == 0 && ITERS >= 1, "tile must be whole iterations");
+    static_assert(SPLIT || (kTileSlots % (kTiledWarps * GPW) == 0 && ITERS >= 1), "tile must be whole iterations");
+    static_assert(!SPLIT || (LP_MAX % GPW == 0 && LP_MAX / GPW <= LPR && !TMA), "SPLIT: one record round, LDG taps");
 
     __shared__ WorkMap wm;
     __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
-    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches, kTiledWarps * GPW);
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, SPLIT ? 0 : allow_patches, kTiledWarps * PPW);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
@@ -234,7 +241,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             unsigned pair; int b, m;
-            const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
+            const bool active = slot_pair<GPW, PPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
             const float2 *st_loc = nullptr; const float *st_attn = nullptr;
             if constexpr (TMA) {
                 const unsigned st = tma_iter & 1u;
@@ -252,10 +259,10 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
             int2 tr[NSL];
 #pragma unroll
             for (int k = 0; k < NSL; ++k) {
-                const int s = sub + k * LPR;
+                const int s = SPLIT ? grp * TPG + sub : sub + k * LPR;
                 tw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 tr[k] = make_int2(0, 0);
-                if (s < LP && active) {
+                if ((!SPLIT || sub < TPG) && s < LP && active) {
                     const size_t t = (size_t)pair * LP + s;
                     const float2 xy = TMA ? st_loc[s] : __ldg(reinterpret_cast<const float2 *>(loc) + t);
                     const float a = TMA ? st_attn[s] : __ldg(attn + t);
@@ -278,7 +285,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                 slab.put(sub, tw[k], tr[k]);
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < LPR; ++j) {
+                for (int j = 0; j < TPG; ++j) {
                     const float4 w = slab.weights(j);
                     const int2 rr = slab.rows(j);
                     const unsigned dwo = (rr.y < 0) ? row_bytes : 0u;
@@ -298,7 +305,14 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                     }
                 }
             }
-            if (active) RowVec<T, VEC>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
+            if constexpr (SPLIT) {                  // the groups hold partial sums over disjoint taps of the same pair
+#pragma unroll
+                for (int d = LPR; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[e] += __shfl_xor_sync(kFullMask, acc[e], d);
+                }
+            }
+            if (active && (!SPLIT || grp == 0)) RowVec<T, VEC>::store(out + (size_t)pair * D + (size_t)sub * VEC, acc);
         }
     }
 }
@@ -333,7 +347,7 @@ __device__ __forceinline__ void group_reduce_scatter(float (&part)[LPR][4], int 
 // Per tap only the four corner dot products  dot_k = sum_c g[c] * V_k[c]  cross lanes; the bilinear coefficients are
 // applied afterwards by the single lane that owns the tap.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA>
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
@@ -343,13 +357,16 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
 {
     constexpr int LPR = D / VEC;
     constexpr int GPW = 32 / LPR;
-    constexpr int NSL = LP_MAX / LPR;
-    constexpr int ITERS = kTileSlots / (kTiledWarps * GPW);
+    constexpr int PPW = SPLIT ? 1 : GPW;                    // see msda_fwd_tiled
+    constexpr int TPG = SPLIT ? LP_MAX / GPW : LPR;
+    constexpr int NSL = SPLIT ? 1 : LP_MAX / LPR;
+    constexpr int ITERS = SPLIT ? 1 : kTileSlots / (kTiledWarps * GPW);
     static_assert(D % VEC == 0 && (LPR & (LPR - 1)) == 0 && LPR <= 32 && LP_MAX % LPR == 0, "bad tiling");
+    static_assert(!SPLIT || (LP_MAX % GPW == 0 && LP_MAX / GPW <= LPR && !TMA), "SPLIT: one record round, LDG taps");
 
     __shared__ WorkMap wm;
     __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
-    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, allow_patches, kTiledWarps * GPW);
+    build_work_map(wm, shapes, lsi, L, N, S, Lq, M, npairs, SPLIT ? 0 : allow_patches, kTiledWarps * PPW);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPR, grp = lane / LPR;
@@ -390,7 +407,7 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             unsigned pair; int b, m;
-            const bool active = slot_pair<GPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
+            const bool active = slot_pair<GPW, PPW>(wm, tc, it, warp, grp, Lq, M, npairs, pair, b, m);
             const float2 *st_loc = nullptr; const float *st_attn = nullptr;
             if constexpr (TMA) {
                 const unsigned st = tma_iter & 1u;
@@ -413,11 +430,11 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
             unsigned tmeta[NSL];                 // corner mask | level << 4
 #pragma unroll
             for (int k = 0; k < NSL; ++k) {
-                const int s = sub + k * LPR;
+                const int s = SPLIT ? grp * TPG + sub : sub + k * LPR;
                 tw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 tr[k] = make_int2(0, 0);
                 tlh[k] = tlw[k] = ta[k] = 0.f; tmeta[k] = 0;
-                if (s < LP && active) {
+                if ((!SPLIT || sub < TPG) && s < LP && active) {
                     const size_t t = (size_t)pair * LP + s;
                     const float2 xy = TMA ? st_loc[s] : __ldg(reinterpret_cast<const float2 *>(loc) + t);
                     const float a = TMA ? st_attn[s] : __ldg(attn + t);
@@ -440,8 +457,12 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                 slab.put(sub, tw[k], tr[k]);
                 __syncwarp();
                 float part[LPR][4];
+                if constexpr (TPG < LPR) {
 #pragma unroll
-                for (int j = 0; j < LPR; ++j) {
+                    for (int j = TPG; j < LPR; ++j) part[j][0] = part[j][1] = part[j][2] = part[j][3] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < TPG; ++j) {
                     const float4 w4 = slab.weights(j);
                     const int2 rr = slab.rows(j);
                     const float w[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -470,9 +491,9 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                 float dot[4];
                 group_reduce_scatter<LPR>(part, sub, dot);
 
-                // ---- the lane that owns tap (sub + k*LPR) finishes it ----
-                const int s = sub + k * LPR;
-                if (s < LP && active) {
+                // ---- the lane that resolved the tap finishes it ----
+                const int s = SPLIT ? grp * TPG + sub : sub + k * LPR;
+                if ((!SPLIT || sub < TPG) && s < LP && active) {
                     const unsigned mk = tmeta[k];
                     const int l = (int)(mk >> 4);
                     const float d0 = (mk & 1u) ? dot[0] : 0.f, d1 = (mk & 2u) ? dot[1] : 0.f;
