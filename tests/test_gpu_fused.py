@@ -89,6 +89,20 @@ def test_sampling_prologue_matches_module_math(refdim, L, P, M, rows):
         assert _rel(g, t.grad) < 1e-4
 
 
+def test_add_layer_norm_under_autocast_is_fp32_like_torch():
+    torch.manual_seed(8)
+    norm = torch.nn.LayerNorm(256).to(DEV)
+    a = torch.randn(4, 300, 256, device=DEV).bfloat16().requires_grad_(True)
+    b = torch.randn(4, 300, 256, device=DEV).bfloat16().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = add_layer_norm(a, b, norm)
+        y_ref = norm(a + b)
+    assert y.dtype == torch.float32 and y_ref.dtype == torch.float32
+    assert _rel(y, y_ref) < 2e-2                      # torch adds in bf16 first; ours adds the fp32 casts
+    y.float().square().mean().backward()
+    assert a.grad.dtype == torch.bfloat16 and torch.isfinite(a.grad.float()).all() and norm.weight.grad is not None
+
+
 def test_linear_colsum_matches_linear():
     torch.manual_seed(3)
     lin = torch.nn.Linear(256, 384).to(DEV)

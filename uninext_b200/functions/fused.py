@@ -118,6 +118,7 @@ def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False, gemm: str = "c
 
 class _SamplingPrologue(Function):
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)      # like the reference module (ms_deform_attn.py:78)
     def forward(ctx, query, w_off, b_off, w_attn, b_attn, ref, shapes, n_heads, n_levels, n_points, gemm):
         lib = _cabi.load()
         q2 = query.reshape(-1, query.shape[-1])
@@ -139,6 +140,7 @@ class _SamplingPrologue(Function):
 
     @staticmethod
     @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_loc, g_attn):
         lib = _cabi.load()
         q2, weight, attn, ref_c, shapes = ctx.saved_tensors
@@ -166,6 +168,7 @@ def sampling_prologue(query, sampling_offsets: torch.nn.Linear, attention_weight
 
 class _AddLayerNorm(Function):
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)      # autocast runs layer_norm in fp32 too
     def forward(ctx, a, b, gamma, beta, eps):
         lib = _cabi.load()
         cols = a.shape[-1]
@@ -184,15 +187,17 @@ class _AddLayerNorm(Function):
                         "msda_add_layernorm_forward_f32")
         ctx.save_for_backward(z, gamma, mean, rstd)
         ctx.has_b = b is not None
+        ctx.a_dtype, ctx.b_dtype = a.dtype, (b.dtype if b is not None else None)
         return y.view(a.shape)
 
     @staticmethod
     @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
         lib = _cabi.load()
         z, gamma, mean, rstd = ctx.saved_tensors
         rows, cols = z.shape
-        gy2 = gy.reshape(rows, cols).contiguous()
+        gy2 = _f32c(gy.reshape(rows, cols))
         dz = torch.empty_like(z)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
@@ -201,14 +206,17 @@ class _AddLayerNorm(Function):
                                                         rstd.data_ptr(), rows, cols, dz.data_ptr(), dgamma.data_ptr(),
                                                         dbeta.data_ptr(), _stream()), "msda_layernorm_backward_f32")
         dz = dz.view(gy.shape)
-        return dz, (dz if ctx.has_b else None), dgamma, dbeta, None
+        da = dz.to(ctx.a_dtype) if ctx.a_dtype != dz.dtype else dz
+        db = (dz.to(ctx.b_dtype) if ctx.b_dtype != dz.dtype else dz) if ctx.has_b else None
+        return da, db, dgamma, dbeta, None
 
 
 def add_layer_norm(a, b, norm: torch.nn.LayerNorm):
     """``norm(a + b)`` (b may be None) as one forward and one backward kernel."""
     cols = a.shape[-1]
-    ok = a.is_cuda and a.dtype == torch.float32 and cols in (128, 256, 384, 512) and norm.elementwise_affine and \
-        norm.bias is not None and not torch.is_autocast_enabled() and (b is None or b.dtype == torch.float32)
+    auto = torch.is_autocast_enabled()               # under autocast the inputs are cast to fp32 by custom_fwd
+    ok = a.is_cuda and (a.dtype == torch.float32 or auto) and cols in (128, 256, 384, 512) and norm.elementwise_affine \
+        and norm.bias is not None and (b is None or b.dtype == torch.float32 or auto)
     if not ok:
         return norm(a if b is None else a + b)
     return _AddLayerNorm.apply(a, b, norm.weight, norm.bias, norm.eps)
