@@ -8,6 +8,10 @@ single hand-written kernels.
                             concatenated weights + one kernel writing loc/attn in the op's layouts.
 * ``linear_colsum``       -- nn.Linear whose bias gradient is one column-sum kernel instead of a generic reduce.
 * ``add_layer_norm``      -- ``LayerNorm(a + b)`` (deformable_transformer.py:354-356,359) forward and backward.
+
+These wrappers are conveniences for the callers of the op: when their preconditions do not hold (non-fp32, CPU tensors,
+unsupported widths) they hand the same maths to the stock torch ops.  The op itself (MSDeformAttnFunction) has no such
+path: it raises without the CUDA library.
 """
 from __future__ import annotations
 
