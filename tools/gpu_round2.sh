@@ -4,7 +4,8 @@ TAG=${1:-r}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 | tee $OUT/pytest_gpu.txt
-echo "== bench" ; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -2 | tee $OUT/bench.txt
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench" ; timeout 900 python bench.py --steps 20 --warmup 5 2>&1 | tail -2 | tee $OUT/bench.txt
 echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_ref.txt
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:msda_ -c 60 --csv --log-file $OUT/launches.csv \
