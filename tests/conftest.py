@@ -21,6 +21,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Build the native libraries when they are missing or stale (a clean checkout has no .so files: they are
+    git-ignored).  This is the test harness building the product, not a fallback: the product itself only loads
+    uninext_b200/lib/libmsda_b200.so and raises when it is absent (tests/test_cabi_symbols.py)."""
+    try:
+        from uninext_b200 import build as _b
+        _b.build()
+        from oracle import msda_oracle as _o
+        _o.build()
+    except Exception as exc:                       # no nvcc / gcc here: the tests that need the libraries will say so
+        print(f"[conftest] native build skipped: {exc}")
+
+
 def golden_names():
     """Op-level golden cases (module-level ones are named module_*.npz and loaded explicitly)."""
     names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
