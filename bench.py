@@ -156,6 +156,12 @@ def samples_per_step(cfg):
 
 
 def run_b200(args):
+    world, rank, local = dist_env()
+    from uninext_b200 import build as _build
+    if local == 0:                       # a clean checkout has no .so (git-ignored): build once per node, like build()
+        _build.build()
+    else:
+        _build.wait_until_built()
     from uninext_b200 import _cabi
     from uninext_b200.dropin import MultiScaleDeformableAttention as MSDA
 

@@ -51,16 +51,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = f"{LIB_PATH}.tmp.{os.getpid()}"          # link under a private name, then rename: readers never see a partial file
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + log)
     if proc.returncode != 0:
         sys.stderr.write(log)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libmsda_b200.so (see output above)")
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(log)
+    return LIB_PATH
+
+
+def wait_until_built(timeout_s: float = 600.0) -> str:
+    """For ranks that do not build: block until another process has produced an up-to-date library."""
+    import time
+    t0 = time.time()
+    while is_stale():
+        if time.time() - t0 > timeout_s:
+            raise RuntimeError(f"{LIB_PATH} was not built within {timeout_s:.0f} s")
+        time.sleep(0.5)
     return LIB_PATH
 
 
