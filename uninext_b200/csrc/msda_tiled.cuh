@@ -20,6 +20,10 @@
 //              (encoder self-attention, deformable_transformer.py:280-292): a tile is one head of an 8x8 pixel patch,
 //              so the rows gathered by neighbouring queries of the same head overlap in L1 while the tile is resident.
 //              Purely a scheduling choice: every pair is still processed exactly once, results do not depend on it.
+//              Off by default (MSDA_PATCHES=1): it raises the L1 hit rate but the kernels are not L1-miss bound.
+// Template switches: TMA   -- stage 1 reads (x, y, a) from a per-warp double buffer filled one iteration ahead by
+//                             cp.async.bulk + mbarrier (linear order only; default on);
+//                    SPLIT -- small launches: the groups of a warp share one pair and split its taps (see kernel body).
 #pragma once
 
 #include "msda_common.cuh"
