@@ -226,19 +226,37 @@ def test_full_size_grad_value_vs_oracle_fp32():
     assert _maxerr(n(ga), ga_t.astype(np.float64)) < 1e-4
 
 
-def test_full_size_bf16_cfg3():
-    cfg = CONFIGS["cfg3"]
-    inp = make_inputs(cfg, "enc", DEV, dtype=torch.bfloat16, seed=11)
+@pytest.mark.parametrize("cfgname,kind", [("cfg3", "enc"), ("cfg3", "dec"), ("cfg4", "enc"), ("cfg4", "dec"),
+                                          ("cfg5", "enc"), ("cfg5", "dec")])
+def test_full_size_bf16_vs_oracle(cfgname, kind):
+    """BASELINE.json's bf16 configurations (cfg3 / cfg4 / cfg5), encoder- and decoder-shaped calls, against the ORACLE
+    (not against another kernel of this repo): out / grad_loc / grad_attn on a strided query subset against the fp64 C
+    oracle, the whole grad_value against the C oracle run over every query on the host cores.  The oracle sees the
+    same bf16-rounded value / grad_output; tolerance 1e-2 of scale (north_star) covers the bf16 rounding of the
+    stored results."""
+    cfg = CONFIGS[cfgname]
+    inp = make_inputs(cfg, kind, DEV, dtype=torch.bfloat16, seed=11, wild_fraction=0.05)
     a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"],
          inp["attention_weights"])
+    assert _cabi.load().msda_uses_fast_path(2, a[0].shape[3], a[1].shape[0], a[3].shape[4]) == 1
     out = MSDA.ms_deform_attn_forward(*a, 64)
-    ref = MSDA.ms_deform_attn_forward(inp["value"].float(), *a[1:], 64)       # fp32 kernel on the same bf16 values
-    assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
     gv, gl, ga = MSDA.ms_deform_attn_backward(*a, inp["grad_output"], 64)
-    gv32, gl32, ga32 = MSDA.ms_deform_attn_backward(inp["value"].float(), *a[1:], inp["grad_output"].float(), 64)
-    assert (gv.float() - gv32).abs().max().item() < 1e-2 * gv32.abs().max().item()
-    assert (gl - gl32).abs().max().item() < 1e-3 * gl32.abs().max().item()
-    assert (ga - ga32).abs().max().item() < 1e-3 * ga32.abs().max().item()
+    assert out.dtype == torch.bfloat16 and gv.dtype == torch.bfloat16
+    Lq = a[3].shape[1]
+    idx = torch.arange(0, Lq, max(1, Lq // 257), device=DEV)
+    sub = dict(inp)
+    sub["sampling_locations"] = a[3][:, idx].contiguous()
+    sub["attention_weights"] = a[4][:, idx].contiguous()
+    sub["grad_output"] = inp["grad_output"][:, idx].contiguous()
+    out_t, _, gl_t, ga_t = _oracle_truth(sub)
+    n = lambda t: t.float().cpu().numpy()
+    assert _maxerr(n(out[:, idx]), out_t) < 1e-2
+    assert _gl_ok(n(gl[:, idx]), gl_t, 2e-2)
+    assert _maxerr(n(ga[:, idx]), ga_t) < 1e-2
+    # whole grad_value: every query contributes, so the oracle runs at full size (fp32 C, OpenMP over the host cores)
+    gv_t, _, _ = msda_oracle.backward(n(inp["grad_output"]), n(a[0]), a[1].cpu().numpy(), a[2].cpu().numpy(),
+                                      n(a[3]), n(a[4]))
+    assert _maxerr(n(gv), gv_t.astype(np.float64)) < 1e-2
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -18,25 +18,71 @@ def _add_pos(x, pos):
     return x if pos is None else x + pos
 
 
+def fp32_under_autocast(forward):
+    """The reference decorates every forward on the path with ``@custom_fwd(cast_inputs=torch.float32)``
+    (deformable_transformer.py:351,398; _dino.py:360,407,441,511): inside autocast the WHOLE layer -- FFN GEMMs
+    included -- runs in fp32 with autocast off.  Mirrored here for the reference-compatible configuration
+    (``op_dtype is None``); with ``op_dtype=torch.bfloat16`` (new, no reference counterpart) autocast is left on."""
+    import functools
+
+    @functools.wraps(forward)
+    def wrapper(self, *args, **kwargs):
+        if getattr(self, "op_dtype", None) is None and torch.is_autocast_enabled("cuda"):
+            cast = lambda t: t.float() if torch.is_tensor(t) and t.is_cuda and t.is_floating_point() else t
+            with torch.autocast("cuda", enabled=False):
+                return forward(self, *[cast(a) for a in args], **{k: cast(v) for k, v in kwargs.items()})
+        return forward(self, *args, **kwargs)
+    return wrapper
+
+
+def _activation(name):
+    """deformable_transformer.py `_get_activation_fn`: relu / gelu / glu, anything else raises."""
+    import torch.nn.functional as F
+    if name not in ("relu", "gelu", "glu"):
+        raise RuntimeError(f"activation should be relu/gelu, not {name}.")
+    return getattr(F, name)
+
+
+def _ffn(x, linear1, act_name, drop_a, linear2):
+    """linear2(dropout(activation(linear1(x)))) -- forward_ffn of both layers (deformable_transformer.py:345-349,
+    392-396).  ReLU (every UNINEXT config) rides in the first GEMM's epilogue."""
+    if act_name == "relu":
+        return linear_colsum(drop_a(linear_colsum(x, linear1, relu=True)), linear2)
+    return linear_colsum(drop_a(_activation(act_name)(linear_colsum(x, linear1))), linear2)
+
+
 class DeformableTransformerEncoderLayer(nn.Module):
-    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+    """Constructor arguments in the reference's order (deformable_transformer.py:322-325); ``op_dtype`` is new."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 op_dtype=None):
         super().__init__()
+        _activation(activation)
+        self.activation_name = activation
+        self.op_dtype = op_dtype
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, op_dtype=op_dtype)
         self.dropout1, self.norm1 = nn.Dropout(dropout), nn.LayerNorm(d_model)
         self.linear1, self.dropout2 = nn.Linear(d_model, d_ffn), nn.Dropout(dropout)
         self.linear2, self.dropout3 = nn.Linear(d_ffn, d_model), nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
 
+    @fp32_under_autocast
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         att = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
         src = add_layer_norm(src, self.dropout1(att), self.norm1)
-        ffn = linear_colsum(self.dropout2(linear_colsum(src, self.linear1, relu=True)), self.linear2)
+        ffn = _ffn(src, self.linear1, self.activation_name, self.dropout2, self.linear2)
         return add_layer_norm(src, self.dropout3(ffn), self.norm2)
 
 
 class DeformableTransformerDecoderLayer(nn.Module):
-    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4, op_dtype=None):
+    """Constructor arguments in the reference's order (deformable_transformer.py:365-368); ``op_dtype`` is new."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 op_dtype=None):
         super().__init__()
+        _activation(activation)
+        self.activation_name = activation
+        self.op_dtype = op_dtype
         self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points, op_dtype=op_dtype)
         self.dropout1, self.norm1 = nn.Dropout(dropout), nn.LayerNorm(d_model)
         self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
@@ -45,15 +91,19 @@ class DeformableTransformerDecoderLayer(nn.Module):
         self.linear2, self.dropout4 = nn.Linear(d_ffn, d_model), nn.Dropout(dropout)
         self.norm3 = nn.LayerNorm(d_model)
 
+    @fp32_under_autocast
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None):
+                src_padding_mask=None, attn_masks=None):
+        """``attn_masks``: the DINO variant's self-attention mask over the queries (denoising groups must not see each
+        other; deformable_transformer_dino.py:407-412).  The non-DINO layer (deformable_transformer.py:398-401) is
+        the same call with ``attn_masks=None``."""
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
-        sa = self.self_attn(qk, qk, tgt.transpose(0, 1))[0].transpose(0, 1)
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), attn_mask=attn_masks)[0].transpose(0, 1)
         tgt = add_layer_norm(tgt, self.dropout2(sa), self.norm2)
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes, level_start_index,
                              src_padding_mask)
         tgt = add_layer_norm(tgt, self.dropout1(ca), self.norm1)
-        ffn = linear_colsum(self.dropout3(linear_colsum(tgt, self.linear1, relu=True)), self.linear2)
+        ffn = _ffn(tgt, self.linear1, self.activation_name, self.dropout3, self.linear2)
         return add_layer_norm(tgt, self.dropout4(ffn), self.norm3)
 
 

@@ -1,0 +1,148 @@
+"""The pieces of the DINO-style deformable transformer that sit directly on the op's callers
+(deformable_transformer_dino.py): the ReID head (two more decoder layers on detached queries, video configs), the
+reference-point / proposal generators that feed the op, and the small position-embedding helpers they use.
+
+Sub-module and parameter names are the reference's, so its checkpoints load unchanged:
+    DeformableReidHead:   layers.{i}.<decoder layer>, ref_point_head.layers.{0,1}        (_dino.py:504-527)
+    MLP:                  layers.{i}                                                       (_dino.py:589-609)
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .deformable_layers import fp32_under_autocast
+
+
+class MLP(nn.Module):
+    """Linear -> ReLU -> ... -> Linear (deformable_transformer_dino.py:575-609)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, num_layers: int):
+        super().__init__()
+        self.num_layers = num_layers
+        dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.layers = nn.ModuleList(nn.Linear(i, o) for i, o in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = layer(x)
+            if i < self.num_layers - 1:
+                x = F.relu(x)
+        return x
+
+
+def get_sine_pos_embed(pos_tensor: torch.Tensor, num_pos_feats: int = 128, temperature: int = 10000,
+                       exchange_xy: bool = True) -> torch.Tensor:
+    """[.., Q, n] positions in [0, 1] -> [.., Q, n * num_pos_feats] sine embedding (deformable_transformer_dino.py:612-646):
+    component k, feature j = sin / cos (j even / odd) of ``pos_k * 2*pi / temperature ** (2 * (j // 2) / num_pos_feats)``;
+    with ``exchange_xy`` the y block comes first."""
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=pos_tensor.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    arg = pos_tensor.unsqueeze(-1) * (2 * math.pi) / dim_t                         # [.., n, F]
+    emb = torch.stack((arg[..., 0::2].sin(), arg[..., 1::2].cos()), dim=-1).flatten(-2)
+    order = list(range(pos_tensor.shape[-1]))
+    if exchange_xy and len(order) >= 2:
+        order[0], order[1] = 1, 0
+    return emb[..., order, :].flatten(-2)
+
+
+def valid_ratios_from_masks(masks):
+    """Per level ``(valid_W / W, valid_H / H)`` from the padding masks [N, H_l, W_l] -> [N, L, 2]
+    (get_valid_ratio, deformable_transformer_dino.py:164-171)."""
+    out = []
+    for m in masks:
+        _, h, w = m.shape
+        vh = (~m[:, :, 0]).sum(1).float() / h
+        vw = (~m[:, 0, :]).sum(1).float() / w
+        out.append(torch.stack((vw, vh), -1))
+    return torch.stack(out, 1)
+
+
+_PIXEL_CENTRES = {}
+
+
+def _pixel_centres(shapes_key, device):
+    """Un-normalised pixel centres (x + 0.5, y + 0.5) and (W_l, H_l) per flattened pyramid position: constants of the
+    pyramid, built once per (shapes, device)."""
+    key = (shapes_key, str(device))
+    hit = _PIXEL_CENTRES.get(key)
+    if hit is None:
+        xy, wh = [], []
+        for h, w in shapes_key:
+            ys = torch.arange(h, dtype=torch.float32, device=device) + 0.5
+            xs = torch.arange(w, dtype=torch.float32, device=device) + 0.5
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            xy.append(torch.stack((xx.reshape(-1), yy.reshape(-1)), -1))
+            wh.append(torch.tensor([float(w), float(h)], device=device).expand(h * w, 2))
+        lvl = torch.cat([torch.full((h * w,), i, dtype=torch.long, device=device) for i, (h, w) in enumerate(shapes_key)])
+        hit = _PIXEL_CENTRES[key] = (torch.cat(xy), torch.cat(wh), lvl)
+    return hit
+
+
+def _shapes_key(spatial_shapes):
+    if torch.is_tensor(spatial_shapes):
+        spatial_shapes = spatial_shapes.tolist()
+    return tuple((int(h), int(w)) for h, w in spatial_shapes)
+
+
+def get_reference_points(spatial_shapes, valid_ratios, device=None):
+    """Encoder reference points [N, S, L, 2] (deformable_transformer_dino.py:289-301): pixel centre of every pyramid
+    position, normalised by the valid extent of ITS level, then scaled by every level's valid ratio.  The pixel grid is
+    a constant of ``spatial_shapes`` and is cached; per call only one divide and one multiply remain."""
+    device = device or valid_ratios.device
+    xy, wh, lvl = _pixel_centres(_shapes_key(spatial_shapes), device)
+    ref = xy[None] / (valid_ratios[:, lvl] * wh[None])                  # [N, S, 2]
+    return ref[:, :, None] * valid_ratios[:, None]
+
+
+def gen_encoder_output_proposals(memory_padding_mask, spatial_shapes, base_scale: float = 0.05):
+    """Two-stage proposals from the pyramid geometry (the part of deformable_transformer_dino.py:132-162 that does not
+    touch learned weights): -> (output_proposals [N, S, 4] in logit space, +inf where padded or outside (0.01, 0.99);
+    keep [N, S, 1] bool = positions whose memory survives).  The caller applies ``enc_output`` / ``enc_output_norm`` to
+    ``memory.masked_fill(~keep, 0)``."""
+    shapes = _shapes_key(spatial_shapes)
+    n = memory_padding_mask.shape[0]
+    device = memory_padding_mask.device
+    xy, wh, lvl = _pixel_centres(shapes, device)
+    counts, cur = [], 0
+    for h, w in shapes:
+        m = memory_padding_mask[:, cur:cur + h * w].view(n, h, w)
+        counts.append(torch.stack(((~m[:, 0, :]).sum(1), (~m[:, :, 0]).sum(1)), -1))          # (valid_W, valid_H)
+        cur += h * w
+    valid = torch.stack(counts, 1).float()                                                       # [N, L, 2]
+    grid = xy[None] / valid[:, lvl]                                    # (x + 0.5) / valid_W, (y + 0.5) / valid_H
+    size = (base_scale * (2.0 ** lvl.float()))[None, :, None].expand(n, -1, 2)
+    prop = torch.cat((grid, size), -1)
+    ok = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
+    prop = torch.log(prop / (1 - prop))
+    keep = ok & ~memory_padding_mask.unsqueeze(-1)
+    return prop.masked_fill(~keep, float("inf")), keep
+
+
+class DeformableReidHead(nn.Module):
+    """Two (``num_layers``) more decoder layers over the encoder memory, fed with detached decoder queries and their
+    boxes (deformable_transformer_dino.py:504-527; ddetrs_vid.py calls it once per key / reference frame)."""
+
+    def __init__(self, embed_dim, decoder_layer, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList(copy.deepcopy(decoder_layer) for _ in range(num_layers))
+        self.num_layers = num_layers
+        self.ref_point_head = MLP(2 * embed_dim, embed_dim, embed_dim, 2)
+        self.op_dtype = getattr(decoder_layer, "op_dtype", None)
+
+    @fp32_under_autocast
+    def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
+                query_pos=None, src_padding_mask=None, attn_masks=None):
+        if reference_points.shape[-1] != 4:
+            raise ValueError("reference_points.shape[-1] should be 4")
+        ref_in = reference_points[:, :, None] * torch.cat((src_valid_ratios, src_valid_ratios), -1)[:, None]
+        query_pos = self.ref_point_head(get_sine_pos_embed(ref_in[:, :, 0, :]))      # the same for every layer
+        output = tgt
+        for layer in self.layers:
+            output = layer(output, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index,
+                           src_padding_mask, attn_masks)
+        return output
