@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frames", action="store_true", help="skip the whole-model frames/s measurement")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the reference's own CUDA kernels")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config (cfg3/4/5 bf16) kernel table")
     ap.add_argument("--frames-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="target CPU seconds for the cpu_baseline sample")
     return ap.parse_args()
@@ -273,6 +275,14 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(cfg, args.cpu_budget_s)
 
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_reference_cuda and args.dtype == "fp32":
+        ref_cuda = reference_cuda_leg(calls, op_args, kern)
+
+    other_cfgs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        other_cfgs = other_configs_leg(MSDA, device, peak)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K,
@@ -290,12 +300,75 @@ def run_b200(args):
                                "dec_fwd": round(cfg.samples("dec") / kern["dec_fwd_ms"] / 1e6, 2),
                                "dec_bwd": round(cfg.samples("dec") / kern["dec_bwd_ms"] / 1e6, 2)},
             "roofline": roofline, "e2e": e2e, "frames": frames, "gpu_launches": int(launches), "clocks": clocks,
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": cpu_base, "reference_cuda": ref_cuda, "configs": other_cfgs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def _time_call(fn, iters=10, warm=3):
+    """Median CUDA-event time of fn() over `iters` runs, with a 256 MB write between runs to flush the 126 MB L2."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    xs = []
+    for i in range(warm + iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            xs.append(e0.elapsed_time(e1))
+    return statistics.median(xs)
+
+
+def reference_cuda_leg(calls, op_args, kern):
+    """The REAL bar: the reference's own CUDA kernels -- ms_deform_im2col_cuda.cuh compiled unmodified
+    for sm_100a into oracle/_ref (oracle/build_refcuda.sh) -- timed on the same tensors of the same B200, OUTSIDE the
+    timed region of this bench.  oracle/ is used here only as a measured baseline, like cpu_baseline."""
+    try:
+        from oracle import refcuda
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:160]}
+    if not refcuda.available():
+        return {"unavailable": "oracle/_ref/libmsda_refcuda.so not built (needs /root/reference at build time)"}
+    res = {"what": "reference kernels ms_deformable_im2col_gpu_kernel / ms_deformable_col2im_gpu_kernel_shm_blocksize_aware_"
+                   "reduce_v1<float,32> incl. the reference wrapper's zero-fills (at::zeros, cu:54,121-123); median of 10, L2 "
+                   "flushed; not part of `value`"}
+    for kind in ("enc", "dec"):
+        c = next(x for x in calls if x["kind"] == kind)
+        a = op_args(c)
+        outs = (torch.empty_like(a[0]), torch.empty_like(a[3]), torch.empty_like(a[4]))
+        f = _time_call(lambda: refcuda.forward(*a))
+        b = _time_call(lambda: refcuda.backward(*a, c["grad_output"], outs=outs))
+        res[kind] = {"ref_fwd_ms": round(f, 4), "ref_bwd_ms": round(b, 4),
+                     "ours_fwd_ms": round(kern[f"{kind}_fwd_ms"], 4), "ours_bwd_ms": round(kern[f"{kind}_bwd_ms"], 4),
+                     "speedup_fwd": round(f / kern[f"{kind}_fwd_ms"], 2), "speedup_bwd": round(b / kern[f"{kind}_bwd_ms"], 2)}
+    return res
+
+
+def other_configs_leg(MSDA, device, peak):
+    """BASELINE.json configs[2..4] (bf16): encoder- and decoder-shaped call times and the HBM-roofline fraction of the
+    encoder-shaped ones (algorithmic bytes / time / measured peak).  Parity for these shapes: tests/test_gpu_parity.py."""
+    res = {}
+    for name in ("cfg3", "cfg4", "cfg5"):
+        cfg = CONFIGS[name]
+        row = {"workload": cfg.name, "dtype": "bf16"}
+        for kind in ("enc", "dec"):
+            c = make_inputs(cfg, kind, device, dtype=torch.bfloat16, seed=7)
+            a = (c["value"], c["spatial_shapes"], c["level_start_index"], c["sampling_locations"], c["attention_weights"])
+            f = _time_call(lambda: MSDA.ms_deform_attn_forward(*a, 64))
+            b = _time_call(lambda: MSDA.ms_deform_attn_backward(*a, c["grad_output"], 64))
+            smp = cfg.samples(kind)
+            row[kind] = {"fwd_ms": round(f, 4), "bwd_ms": round(b, 4),
+                         "gsamples_per_s_fwd_bwd": round(smp / (f + b) / 1e6, 2),
+                         "frac_fwd": round(algorithmic_bytes(cfg, kind, 2, "fwd") / (f * 1e-3) / 1e9 / peak, 4),
+                         "frac_bwd": round(algorithmic_bytes(cfg, kind, 2, "bwd") / (b * 1e-3) / 1e9 / peak, 4)}
+            del c, a
+        res[name] = row
+    return res
 
 
 def run_frames(cfg, world, rank, device, steps, barrier, lib):
