@@ -57,6 +57,22 @@ int msda_uses_fast_path(int dtype_bytes, int D, int L, int P);
 /* Number of kernel launches (memsets excluded) this process has issued through this library. */
 uint64_t msda_launch_count(void);
 
+/* Kernel-selection knobs (process-wide; initial values come from the environment variables of the same name with an
+ * MSDA_ prefix, e.g. MSDA_SLAB=0).  They never change results, only which kernel computes them; the tests use
+ * them to run every kernel family on small shapes, the tools to sweep them.  Returns the previous value, or
+ * MSDA_E_BADARG for an unknown knob.  value == MSDA_KNOB_QUERY reads without writing.
+ *   MSDA_KNOB_SLAB          -1 auto (slab-ordered kernels for launches >= 256 pairs per SM), 0 never, 1 whenever D == 32
+ *   MSDA_KNOB_BWD_WIN_ROWS  shared-memory window of the slab backward in rows of 128 B (-1 = all that fits)
+ *   MSDA_KNOB_BWD_LIST_CAP  entries per row-class list of the slab backward (even, >= 8)
+ *   MSDA_KNOB_FWD_SLAB_CTAS resident CTAs per SM of the slab forward (1 or 2) */
+#define MSDA_KNOB_SLAB          0
+#define MSDA_KNOB_BWD_WIN_ROWS  1
+#define MSDA_KNOB_BWD_LIST_CAP  2
+#define MSDA_KNOB_FWD_SLAB_CTAS 3
+#define MSDA_KNOB_COUNT         4
+#define MSDA_KNOB_QUERY         (-1000000)
+int msda_set_knob(int knob, int value);
+
 /* ---- forward: replaces ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80) ---- */
 int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                      const float *sampling_loc, const float *attn_weight,

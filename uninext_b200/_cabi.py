@@ -21,6 +21,7 @@ SIGNATURES = {
     "msda_strerror": (ctypes.c_char_p, [_i]),
     "msda_uses_fast_path": (_i, [_i, _i, _i, _i]),
     "msda_launch_count": (_u64, []),
+    "msda_set_knob": (_i, [_i, _i]),
     "msda_forward_f32": (_i, [_vp] * 5 + _DIMS + [_vp, _vp]),
     "msda_forward_f64": (_i, [_vp] * 5 + _DIMS + [_vp, _vp]),
     "msda_forward_bf16": (_i, [_vp] * 5 + _DIMS + [_vp, _vp]),
@@ -35,6 +36,7 @@ SIGNATURES = {
     "msda_linear_tf32": (_i, [_vp] * 3 + [ctypes.c_int64, _i, _i, _vp, _vp]),
 }
 ABI_VERSION = 1
+KNOB_SLAB, KNOB_BWD_WIN_ROWS, KNOB_BWD_LIST_CAP, KNOB_FWD_SLAB_CTAS = 0, 1, 2, 3      # include/msda_b200.h
 
 _lib = None
 

@@ -8,6 +8,7 @@
 #include "../../include/msda_b200.h"
 #include "msda_generic.cuh"
 #include "msda_module.cuh"
+#include "msda_slab.cuh"
 #include "msda_tiled.cuh"
 
 namespace {
@@ -26,15 +27,45 @@ int check_dims(const Dims &d) {
     return 0;
 }
 
-int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    return sms;
+// Per-device caches (a process may drive several GPUs: SM counts, occupancy and function attributes are per device).
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
 }
+
+int num_sms() {
+    static std::atomic<int> sms[kMaxDevices];
+    const int dev = current_device();
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+// Kernel-selection knobs (msda_set_knob): environment defaults, overridable at run time.  g_knob_epoch invalidates the
+// per-device launch configurations derived from them.
+struct Knobs {
+    std::atomic<int> v[MSDA_KNOB_COUNT];
+    std::atomic<int> epoch{1};
+    Knobs() {
+        v[MSDA_KNOB_SLAB].store(env_int("MSDA_SLAB", -1));
+        v[MSDA_KNOB_BWD_WIN_ROWS].store(env_int("MSDA_BWD_WIN_ROWS", -1));
+        v[MSDA_KNOB_BWD_LIST_CAP].store(env_int("MSDA_BWD_LIST_CAP", 48));
+        v[MSDA_KNOB_FWD_SLAB_CTAS].store(env_int("MSDA_FWD_SLAB_CTAS", 2));
+    }
+};
+Knobs &knobs() { static Knobs k; return k; }
+int knob(int i) { return knobs().v[i].load(std::memory_order_relaxed); }
 
 // ---- routing ------------------------------------------------------------------------------------------------
 // Fast path: D in {16,32,64} (fp32) / {32,64} (bf16), L <= kMaxLevels, L*P <= 32.  LP_MAX is the compile-time tap
@@ -58,6 +89,15 @@ int resident_ctas(K kernel) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, msda::kTiledThreads, 0) != cudaSuccess || per_sm < 1)
         per_sm = 1;
     return per_sm * num_sms();
+}
+
+// resident_ctas() cached per (kernel instantiation, device)
+template <typename K>
+int resident_ctas_cached(K kernel, std::atomic<int> (&cache)[kMaxDevices]) {
+    const int dev = current_device();
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) { v = resident_ctas(kernel); cache[dev].store(v, std::memory_order_relaxed); }
+    return v;
 }
 
 // Slot order.  Measured on B200 (profiles/r01c_*_ncu.md, gpurun_out r01d sweep): the 8x8-pixel patch order lifts the
@@ -109,10 +149,10 @@ cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi
     auto kern = split ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>
                 : tma ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>
                       : msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>;
-    static int slots_split = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>);
-    static int slots_tma = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>);
-    static int slots_ldg = resident_ctas(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>);
-    int slots = split ? slots_split : tma ? slots_tma : slots_ldg;
+    static std::atomic<int> c_split[kMaxDevices], c_tma[kMaxDevices], c_ldg[kMaxDevices];
+    const int slots = split ? resident_ctas_cached(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>, c_split)
+                      : tma ? resident_ctas_cached(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>, c_tma)
+                            : resident_ctas_cached(msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>, c_ldg);
     const unsigned iter_pairs = msda::kTiledWarps * (split ? 1 : GPW);
     const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;        // linear order (patch order has fewer, larger tiles)
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
@@ -135,15 +175,80 @@ cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes,
     auto kern = split ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, kCanSplit>
                 : tma ? msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage, false>
                       : msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, false>;
-    static int slots_split = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, kCanSplit>);
-    static int slots_tma = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage, false>);
-    static int slots_ldg = resident_ctas(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, false>);
-    int slots = split ? slots_split : tma ? slots_tma : slots_ldg;
+    static std::atomic<int> c_split[kMaxDevices], c_tma[kMaxDevices], c_ldg[kMaxDevices];
+    const int slots = split ? resident_ctas_cached(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, kCanSplit>, c_split)
+                      : tma ? resident_ctas_cached(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, kCanStage, false>, c_tma)
+                            : resident_ctas_cached(msda::msda_bwd_tiled<T, VEC, D, LP_MAX, kBwdMinCtas, false, false>, c_ldg);
     const unsigned iter_pairs = msda::kTiledWarps * (split ? 1 : GPW);
     const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
                                                npairs, allow_patches(), gv, gl, ga);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// ---- slab-ordered kernels (msda_slab.cuh): large launches with D = 32 and L*P <= 16 (every UNINEXT encoder call) -----
+// MSDA_SLAB=0 / 1 forces the choice (A/B runs); default: launches with at least kSlabMinPairsPerSm pairs per SM.
+constexpr unsigned kSlabMinPairsPerSm = 256;
+
+bool use_slab(const Dims &d, unsigned npairs, const void *value, const void *out) {
+    if (d.D != 32 || d.L * d.P > 16 || d.L > msda::kMaxLevels) return false;
+    if ((reinterpret_cast<uintptr_t>(value) & 31u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return false;   // LDG.256 rows
+    const int force = knob(MSDA_KNOB_SLAB);
+    if (force >= 0) return force == 1;
+    return npairs >= (unsigned)num_sms() * kSlabMinPairsPerSm;
+}
+
+template <typename T>
+cudaError_t launch_fwd_slab(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                            const Dims &d, T *out, cudaStream_t st) {
+    const int ctas_per_sm = knob(MSDA_KNOB_FWD_SLAB_CTAS) == 1 ? 1 : 2;
+    const int sms = num_sms();
+    if (ctas_per_sm == 2)
+        msda::msda_fwd_slab<T, 16, 2><<<sms * 2, msda::kSlabThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L,
+                                                                              d.Lq, d.P, sms, out);
+    else
+        msda::msda_fwd_slab<T, 16, 1><<<sms, msda::kSlabThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L,
+                                                                          d.Lq, d.P, sms, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_bwd_slab(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+                            const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
+    // shared-memory budget: the opt-in maximum of the device minus the kernel's static part; the window gets what the
+    // lists / g stash / tap slabs leave.  MSDA_BWD_WIN_ROWS / MSDA_BWD_LIST_CAP override (sweeps).
+    static std::atomic<int> win_rows[kMaxDevices], cap_c[kMaxDevices], epoch_c[kMaxDevices];
+    const int dev = current_device();
+    const int epoch = knobs().epoch.load(std::memory_order_acquire);
+    int rows = win_rows[dev].load(std::memory_order_relaxed), cap = cap_c[dev].load(std::memory_order_relaxed);
+    auto kern = msda::msda_bwd_slab<T, 16>;
+    if (rows == 0 || epoch_c[dev].load(std::memory_order_relaxed) != epoch) {
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, kern);
+        cap = knob(MSDA_KNOB_BWD_LIST_CAP) & ~1;
+        if (cap < 8) cap = 8;
+        const long long fixed = (long long)msda::bwd_slab_smem_bytes(0, cap) + (long long)fa.sharedSizeBytes + 64;
+        rows = (int)((max_optin - fixed) / 128);
+        const int want = knob(MSDA_KNOB_BWD_WIN_ROWS);
+        if (want >= 0 && want < rows) rows = want;
+        if (rows < 0) rows = 0;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)msda::bwd_slab_smem_bytes(rows, cap));
+        if (e != cudaSuccess) return e;
+        cap_c[dev].store(cap, std::memory_order_relaxed);
+        win_rows[dev].store(rows == 0 ? -1 : rows, std::memory_order_relaxed);
+        epoch_c[dev].store(epoch, std::memory_order_relaxed);
+    }
+    if (rows < 0) rows = 0;
+    const int sms = num_sms();
+    kern<<<sms, msda::kSlabThreads, msda::bwd_slab_smem_bytes(rows, cap), st>>>(grad_out, value, shapes, lsi, loc, attn, d.N,
+                                                                               d.S, d.M, d.L, d.Lq, d.P, sms, rows, cap, gv,
+                                                                               gl, ga);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -155,6 +260,8 @@ template <typename T>
 cudaError_t fwd_fast(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                      const Dims &d, T *out, cudaStream_t st) {
     const int LP = d.L * d.P;
+    if (use_slab(d, (unsigned)((long long)d.N * d.Lq * d.M), value, out))
+        return launch_fwd_slab<T>(value, shapes, lsi, loc, attn, d, out, st);
     switch (d.D) {
         case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st); break;
         case 32: return MSDA_ROUTE_LP(T, 32, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st);
@@ -167,6 +274,8 @@ template <typename T>
 cudaError_t bwd_fast(const T *go, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                      const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
     const int LP = d.L * d.P;
+    if (use_slab(d, (unsigned)((long long)d.N * d.Lq * d.M), value, gv))
+        return launch_bwd_slab<T>(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
     switch (d.D) {
         case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st); break;
         case 32: return MSDA_ROUTE_LP(T, 32, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
@@ -221,6 +330,15 @@ const char *msda_strerror(int code) {
 int msda_uses_fast_path(int dtype_bytes, int D, int L, int P) { return fast_ok(dtype_bytes, D, L, P) ? 1 : 0; }
 
 uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int msda_set_knob(int k, int value) {
+    if (k < 0 || k >= MSDA_KNOB_COUNT) return MSDA_E_BADARG;
+    Knobs &kn = knobs();
+    if (value == MSDA_KNOB_QUERY) return kn.v[k].load(std::memory_order_relaxed);
+    const int old = kn.v[k].exchange(value, std::memory_order_relaxed);
+    kn.epoch.fetch_add(1, std::memory_order_release);
+    return old;
+}
 
 #define MSDA_CHECK_PTRS(...)                                             \
     do {                                                                 \
