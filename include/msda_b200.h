@@ -10,7 +10,9 @@
  * shipped as uninext_b200/dropin/MultiScaleDeformableAttention.py.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer on the current CUDA device, 16-byte aligned, dense row-major:
+ *   - every pointer is a DEVICE pointer on the current CUDA device, dense row-major.  16-byte aligned tensors (what
+ *     any allocator returns) take the tiled / slab sm_100a kernels; a merely element-aligned pointer (a contiguous view
+ *     with a storage offset, which the reference accepts too) is served by the generic kernels:
  *       value              [N, S, M, D]          (reference: ms_deform_attn_cuda.cu:40-43)
  *       spatial_shapes     [L, 2] int64 (H_l,W_l)  -- read on the device, no host sync (cu:67)
  *       level_start_index  [L]    int64            (cu:68)
@@ -43,7 +45,7 @@ extern "C" {
 
 #define MSDA_ABI_VERSION 1
 
-#define MSDA_E_BADARG   (-1)   /* null pointer, non-positive dimension, misaligned pointer            */
+#define MSDA_E_BADARG   (-1)   /* null pointer, non-positive dimension, unknown knob                  */
 #define MSDA_E_TOOLARGE (-2)   /* a dimension product exceeds what the kernels index (see msda_b200.h) */
 #define MSDA_E_NODEVICE (-3)   /* no sm_100 device is current                                          */
 
@@ -61,7 +63,8 @@ uint64_t msda_launch_count(void);
  * MSDA_ prefix, e.g. MSDA_SLAB=0).  They never change results, only which kernel computes them; the tests use
  * them to run every kernel family on small shapes, the tools to sweep them.  Returns the previous value, or
  * MSDA_E_BADARG for an unknown knob.  value == MSDA_KNOB_QUERY reads without writing.
- *   MSDA_KNOB_SLAB          -1 auto (slab-ordered kernels for launches >= 256 pairs per SM), 0 never, 1 whenever D == 32
+ *   MSDA_KNOB_SLAB          1 = slab-ordered kernels (msda_slab.cuh) whenever D == 32 and L*P <= 16; -1 (auto) and 0 = tiled
+ *                           kernels (the measured-faster default)
  *   MSDA_KNOB_BWD_WIN_ROWS  shared-memory window of the slab backward in rows of 128 B (-1 = all that fits)
  *   MSDA_KNOB_BWD_LIST_CAP  entries per row-class list of the slab backward (even, >= 8)
  *   MSDA_KNOB_FWD_SLAB_CTAS resident CTAs per SM of the slab forward (1 or 2) */

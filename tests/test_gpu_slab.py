@@ -2,7 +2,12 @@
 that accumulates the coarse levels of grad_value in a shared-memory window.  At BASELINE sizes they are selected
 automatically (and are what tests/test_gpu_parity.py's full-size cases exercise); here `msda_set_knob` forces them
 onto small and ragged problems so that every branch -- window level sets, list overflow falling back to red.global,
-partial tiles, CTAs spanning several slabs -- is compared with the fp64 oracle and with the tiled kernels."""
+partial tiles, CTAs spanning several slabs -- is compared with the fp64 oracle and with the tiled kernels.
+
+The slab kernels are an OPT-IN family (MSDA_KNOB_SLAB=1): measured on B200 they cut L2 traffic (forward: -48 % L2 sectors,
+L1 hit rate 34 % -> 65 %; backward: -43 % red sectors) but not run time, because the SM's load/store data pipe, not
+L2 or the crossbar, is the wall for both (profiles/r02c_slab_kernels_ncu.md).  They stay tested so the evidence can be
+reproduced."""
 import numpy as np
 import pytest
 import torch
@@ -77,7 +82,7 @@ def test_slab_kernels_vs_oracle_cfg1(knobs, kind, dtype, tol, win_rows, list_cap
     inp = make_inputs(CONFIGS["cfg1"], kind, DEV, dtype=dtype, seed=17, wild_fraction=0.1)
     before = knobs.msda_launch_count()
     _check(inp, tol)
-    assert knobs.msda_launch_count() - before == 2
+    assert knobs.msda_launch_count() - before == (2 if dtype == torch.float32 else 3)      # bf16: + accumulator rounding pass
 
 
 @pytest.mark.parametrize("ctas", [1, 2])
@@ -132,7 +137,7 @@ def test_slab_and_tiled_kernels_agree_at_cfg2(knobs):
     inp = make_inputs(CONFIGS["cfg2"], "enc", DEV, seed=19, wild_fraction=0.02)
     knobs.msda_set_knob(_cabi.KNOB_SLAB, 0)
     ref = _run(inp)
-    knobs.msda_set_knob(_cabi.KNOB_SLAB, -1)         # auto: cfg2 encoder calls are slab launches
+    knobs.msda_set_knob(_cabi.KNOB_SLAB, 1)
     got = _run(inp)
     for i, (a, b) in enumerate(zip(got, ref)):
         scale = b.abs().max().item()

@@ -188,16 +188,17 @@ cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes,
     return cudaGetLastError();
 }
 
-// ---- slab-ordered kernels (msda_slab.cuh): large launches with D = 32 and L*P <= 16 (every UNINEXT encoder call) -----
-// MSDA_SLAB=0 / 1 forces the choice (A/B runs); default: launches with at least kSlabMinPairsPerSm pairs per SM.
-constexpr unsigned kSlabMinPairsPerSm = 256;
+// ---- slab-ordered kernels (msda_slab.cuh): D = 32 and L*P <= 16 (every UNINEXT call) ------------------------------
+// OPT-IN (MSDA_KNOB_SLAB = 1).  Measured at cfg2 (gpurun r02c, profiles/r02c_slab_kernels_ncu.md): forward 0.186 ms against
+// 0.175 ms tiled although L2 sectors halve and the L1 hit rate doubles; backward 0.654 ms against 0.480 ms although red
+// sectors drop 43 % -- the shared-memory traffic of the window (4 wavefronts per privatised row-add) lands on the same
+// LSU data pipe that the gathers already keep > 50 % busy.  MSDA_KNOB_SLAB = -1 (auto) therefore selects the tiled kernels.
 
 bool use_slab(const Dims &d, unsigned npairs, const void *value, const void *out) {
     if (d.D != 32 || d.L * d.P > 16 || d.L > msda::kMaxLevels) return false;
     if ((reinterpret_cast<uintptr_t>(value) & 31u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return false;   // LDG.256 rows
-    const int force = knob(MSDA_KNOB_SLAB);
-    if (force >= 0) return force == 1;
-    return npairs >= (unsigned)num_sms() * kSlabMinPairsPerSm;
+    (void)npairs;
+    return knob(MSDA_KNOB_SLAB) == 1;
 }
 
 template <typename T>
@@ -320,7 +321,7 @@ int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
 const char *msda_strerror(int code) {
     if (code == 0) return "success";
-    if (code == MSDA_E_BADARG) return "msda: bad argument (null/misaligned pointer or non-positive dimension)";
+    if (code == MSDA_E_BADARG) return "msda: bad argument (null pointer, non-positive dimension or unknown knob)";
     if (code == MSDA_E_TOOLARGE) return "msda: problem too large for the kernel index types";
     if (code == MSDA_E_NODEVICE) return "msda: no CUDA device";
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -340,11 +341,17 @@ int msda_set_knob(int k, int value) {
     return old;
 }
 
-#define MSDA_CHECK_PTRS(...)                                             \
+// Null pointers are argument errors.  Alignment is a ROUTING property: the tiled / slab kernels need 16-byte aligned
+// tensors (vector loads, vector reds); anything else -- e.g. a contiguous view with a storage offset, which the
+// reference accepts -- runs on the generic scalar kernels (natural alignment only).
+#define MSDA_CHECK_PTRS(ALIGNED, ...)                                    \
+    bool ALIGNED = true;                                                 \
     do {                                                                 \
         const void *ptrs_[] = {__VA_ARGS__};                             \
-        for (const void *p_ : ptrs_)                                     \
-            if (p_ == nullptr || !aligned16(p_)) return MSDA_E_BADARG;   \
+        for (const void *p_ : ptrs_) {                                   \
+            if (p_ == nullptr) return MSDA_E_BADARG;                     \
+            ALIGNED = ALIGNED && aligned16(p_);                          \
+        }                                                                \
     } while (0)
 
 int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -352,10 +359,10 @@ int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const in
                      int P, float *out, void *stream) {
     const Dims d{N, S, M, D, L, Lq, P};
     if (int e = check_dims(d)) return e;
-    MSDA_CHECK_PTRS(value, sampling_loc, attn_weight, out);
+    MSDA_CHECK_PTRS(al, value, sampling_loc, attn_weight, out);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (use_fast(4, d)) return (int)fwd_fast<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
+    if (al && use_fast(4, d)) return (int)fwd_fast<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
     return (int)fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, out, st);
 }
 
@@ -374,12 +381,12 @@ int msda_forward_bf16(const uint16_t *value, const int64_t *spatial_shapes, cons
                       int P, uint16_t *out, void *stream) {
     const Dims d{N, S, M, D, L, Lq, P};
     if (int e = check_dims(d)) return e;
-    MSDA_CHECK_PTRS(value, sampling_loc, attn_weight, out);
+    MSDA_CHECK_PTRS(al, value, sampling_loc, attn_weight, out);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
-    if (use_fast(2, d)) return (int)fwd_fast<__nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
+    if (al && use_fast(2, d)) return (int)fwd_fast<__nv_bfloat16>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
     return (int)fwd_generic<__nv_bfloat16, float>(v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, o, st);
 }
 
@@ -389,12 +396,12 @@ int msda_backward_f32(const float *grad_out, const float *value, const int64_t *
                       float *grad_attn_weight, void *stream) {
     const Dims d{N, S, M, D, L, Lq, P};
     if (int e = check_dims(d)) return e;
-    MSDA_CHECK_PTRS(grad_out, value, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight);
+    MSDA_CHECK_PTRS(al, grad_out, value, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * S * M * D, st);
     if (err != cudaSuccess) return (int)err;
-    if (use_fast(4, d))
+    if (al && use_fast(4, d))
         return (int)bwd_fast<float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                     grad_value, grad_sampling_loc, grad_attn_weight, st);
     return (int)bwd_generic<float, float, float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
@@ -423,7 +430,7 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
                        float *grad_sampling_loc, float *grad_attn_weight, void *stream) {
     const Dims d{N, S, M, D, L, Lq, P};
     if (int e = check_dims(d)) return e;
-    MSDA_CHECK_PTRS(grad_out, value, sampling_loc, attn_weight, grad_value_f32, grad_sampling_loc, grad_attn_weight);
+    MSDA_CHECK_PTRS(al, grad_out, value, sampling_loc, attn_weight, grad_value_f32, grad_sampling_loc, grad_attn_weight);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t nval = (size_t)N * S * M * D;
@@ -431,7 +438,7 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
     if (err != cudaSuccess) return (int)err;
     const __nv_bfloat16 *go = reinterpret_cast<const __nv_bfloat16 *>(grad_out);
     const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
-    if (use_fast(2, d))
+    if (al && use_fast(2, d))
         err = bwd_fast<__nv_bfloat16>(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                       grad_value_f32, grad_sampling_loc, grad_attn_weight, st);
     else

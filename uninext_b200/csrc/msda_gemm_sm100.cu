@@ -296,17 +296,17 @@ extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bia
     const int need = N * p.acc_bufs;
     p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + kXposeBytes;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
-    });
-    if (attr_err != cudaSuccess) return (int)attr_err;
-    static int sms = 0;
+    // function attributes and SM counts are per DEVICE: cache them per ordinal (a process may drive several GPUs)
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> sms_of[kMaxDev];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) dev = 0;
+    int sms = sms_of[dev].load(std::memory_order_relaxed);
     if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+        cudaError_t attr_err = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+        if (attr_err != cudaSuccess) return (int)attr_err;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        sms_of[dev].store(sms, std::memory_order_relaxed);
     }
     const long long tiles = (M + BLOCK_M - 1) / BLOCK_M, pairs = (tiles + 1) / 2;
     const long long max_clusters = sms / 2;

@@ -77,8 +77,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step):
-    """-> [grad_value, grad_sampling_loc, grad_attn_weight]   (reference ms_deform_attn_cuda_backward, cu:83-153)."""
+                            im2col_step, grad_value_dtype=None):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]   (reference ms_deform_attn_cuda_backward, cu:83-153).
+    ``grad_value_dtype=torch.float32`` (bf16 ``value`` only, beyond the reference): hand back the fp32 accumulator
+    itself instead of its bf16 rounding -- no conversion pass, no second buffer."""
     _checks([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
              ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)],
             value, im2col_step)
@@ -96,9 +98,10 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
                   sampling_loc.data_ptr(), attn_weight.data_ptr(), *dims)
         if value.dtype == torch.bfloat16:
             acc = torch.empty(value.shape, dtype=torch.float32, device=value.device)
-            grad_value = torch.empty_like(value)
-            code = lib.msda_backward_bf16(*common, acc.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(),
-                                          grad_attn.data_ptr(), stream)
+            keep_f32 = grad_value_dtype == torch.float32
+            grad_value = acc if keep_f32 else torch.empty_like(value)
+            code = lib.msda_backward_bf16(*common, acc.data_ptr(), None if keep_f32 else grad_value.data_ptr(),
+                                          grad_loc.data_ptr(), grad_attn.data_ptr(), stream)
         else:
             grad_value = torch.empty_like(value)          # zero-filled by the callee (cudaMemsetAsync on `stream`)
             fn = getattr(lib, "msda_backward_" + _SUFFIX[value.dtype])

@@ -45,6 +45,7 @@ class MSDeformAttnFunctionBF16(Function):
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
                 im2col_step):
         ctx.im2col_step = im2col_step
+        ctx.value_dtype = value.dtype            # an fp32 value_proj output gets the fp32 accumulator back, un-rounded
         value = value.to(torch.bfloat16)
         loc = sampling_locations.float().contiguous()
         attn = attention_weights.float().contiguous()
@@ -59,5 +60,6 @@ class MSDeformAttnFunctionBF16(Function):
     def backward(ctx, grad_output):
         value, shapes, lsi, loc, attn = ctx.saved_tensors
         grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
-            value, shapes, lsi, loc, attn, grad_output.to(torch.bfloat16).contiguous(), ctx.im2col_step)
-        return grad_value, None, None, grad_loc.to(ctx.loc_dtype), grad_attn.to(ctx.attn_dtype), None
+            value, shapes, lsi, loc, attn, grad_output.to(torch.bfloat16).contiguous(), ctx.im2col_step,
+            grad_value_dtype=torch.float32 if ctx.value_dtype == torch.float32 else None)
+        return grad_value.to(ctx.value_dtype), None, None, grad_loc.to(ctx.loc_dtype), grad_attn.to(ctx.attn_dtype), None
