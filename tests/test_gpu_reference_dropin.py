@@ -24,8 +24,8 @@ if torch.cuda.is_available():
     from uninext_b200.modules import MSDeformAttn
     from uninext_b200.modules.deformable_layers import (DeformableTransformerDecoderLayer,
                                                         DeformableTransformerEncoderLayer)
-    from uninext_b200.modules.deformable_transformer import (DeformableReidHead, get_reference_points,
-                                                             valid_ratios_from_masks)
+    from uninext_b200.modules.deformable_transformer import (MLP, DeformableReidHead, DeformableTransformerDecoder,
+                                                             get_reference_points, valid_ratios_from_masks)
     from uninext_b200.workloads import CONFIGS, level_tensors, make_inputs
 
 DEV = "cuda"
@@ -182,6 +182,59 @@ def test_reference_reid_head_on_dropin(ref):
             layer.cross_attn.attention_weights.weight.normal_(0, 0.05)
     ours = DeformableReidHead(256, DeformableTransformerDecoderLayer(256, 512, 0.0, "relu", 4, 8, 4), 2).to(DEV)
     _compare(ours, theirs, lambda m, t, x: m(t, boxes, x, ss, lsi, vr, None, flat, None), [tgt, src])
+
+
+@pytest.mark.parametrize("refine", [True, False])
+def test_reference_decoder_loop_on_dropin(ref, refine):
+    """The whole DINO decoder loop (sine embedding -> ref_point_head -> layer -> box refinement, look_forward_twice),
+    reference class on the drop-in against this repo's decoder, which projects the memory for all layers in ONE batched
+    GEMM."""
+    g = torch.Generator().manual_seed(80)
+    n, q, nl = 2, 23, 3
+    ss, lsi, masks, flat, src, _ = _pyramid_inputs(n, g)
+    vr = valid_ratios_from_masks(masks)
+    tgt, _, boxes = _decoder_inputs(n, q, g)
+    dino = ref[3]
+    torch.manual_seed(6)
+    theirs = dino.DeformableTransformerDecoder(256, dino.DeformableTransformerDecoderLayer(256, 512, 0.0, "relu", 4, 8, 4), nl,
+                                               return_intermediate=True, look_forward_twice=refine).to(DEV)
+    ours = DeformableTransformerDecoder(256, DeformableTransformerDecoderLayer(256, 512, 0.0, "relu", 4, 8, 4), nl,
+                                        return_intermediate=True, look_forward_twice=refine).to(DEV)
+    if refine:          # the detector attaches the box heads to the decoder (iterative refinement), as the reference does
+        theirs.bbox_embed = torch.nn.ModuleList(dino.MLP(256, 256, 4, 3) for _ in range(nl)).to(DEV)
+        ours.bbox_embed = torch.nn.ModuleList(MLP(256, 256, 4, 3) for _ in range(nl)).to(DEV)
+    with torch.no_grad():
+        for layer in theirs.layers:
+            layer.cross_attn.sampling_offsets.weight.normal_(0, 0.02)
+            layer.cross_attn.attention_weights.weight.normal_(0, 0.05)
+
+    def run(m, t, x):
+        hs, refs = m(t, boxes, x, ss, lsi, vr, None, flat, None)
+        return torch.cat((hs.flatten(), refs.flatten()))
+    _compare(ours, theirs, run, [tgt, src])
+
+
+def test_batched_value_proj_equals_per_layer_projection():
+    from uninext_b200.modules.ms_deform_attn import batched_value_proj
+    g = torch.Generator().manual_seed(81)
+    ss, lsi, masks, flat, src, _ = _pyramid_inputs(2, g)
+    torch.manual_seed(7)
+    mods = [MSDeformAttn(256, 4, 8, 4).to(DEV) for _ in range(3)]
+    x = src.clone().requires_grad_(True)
+    vals = batched_value_proj(mods, x, flat)
+    want = [m.value_proj(src).masked_fill(flat[..., None], 0.0) for m in mods]
+    for a, b in zip(vals, want):
+        assert _rel(a, b) < 1e-5
+    sum((v * (i + 1)).sum() for i, v in enumerate(vals)).backward()
+    gw = [m.value_proj.weight.grad.clone() for m in mods]
+    gx = x.grad.clone()
+    for m in mods:
+        m.zero_grad()
+    x2 = src.clone().requires_grad_(True)
+    sum((m.value_proj(x2).masked_fill(flat[..., None], 0.0) * (i + 1)).sum() for i, m in enumerate(mods)).backward()
+    assert _rel(gx, x2.grad) < 1e-4
+    for a, m in zip(gw, mods):
+        assert _rel(a, m.value_proj.weight.grad) < 1e-4
 
 
 def test_layers_run_fp32_under_autocast_like_reference(ref):

@@ -120,6 +120,41 @@ def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False, gemm: str = "c
     return _LinearColsum.apply(x, linear.weight, linear.bias, relu, gemm)
 
 
+class _BatchedLinear(Function):
+    """y[l] = x2 @ w[l].T + b[l] for l = 0..L-1 as one strided-batched GEMM over a shared A operand."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x2, w, b):
+        L, n, k = w.shape
+        y = torch.baddbmm(b[:, None, :], x2.unsqueeze(0).expand(L, -1, -1), w.transpose(1, 2))        # [L, R, n]
+        ctx.save_for_backward(x2, w)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        L = w.shape[0]
+        g = g.contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(g[0], w[0])
+            for i in range(1, L):
+                gx.addmm_(g[i], w[i])                          # accumulate in place: no [L, R, K] temporary
+        gw = torch.stack([weight_grad(g[i], x2) for i in range(L)]) if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            gb = torch.stack([colsum(g[i]) for i in range(L)]) if g.is_cuda and g.dtype == torch.float32 else g.sum(1)
+        return gx, gw, gb
+
+
+def batched_linear(x2, w, b):
+    """x2 [R, K], w [L, N, K], b [L, N] -> [L, R, N]."""
+    return _BatchedLinear.apply(x2, w, b)
+
+
 class _SamplingPrologue(Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)      # like the reference module (ms_deform_attn.py:78)

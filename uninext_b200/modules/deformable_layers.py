@@ -11,7 +11,7 @@ from torch import nn
 
 from uninext_b200.functions.fused import add_layer_norm, linear_colsum
 
-from .ms_deform_attn import MSDeformAttn
+from .ms_deform_attn import MSDeformAttn, batched_value_proj
 
 
 def _add_pos(x, pos):
@@ -93,15 +93,16 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     @fp32_under_autocast
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None, attn_masks=None):
+                src_padding_mask=None, attn_masks=None, *, projected_value=None):
         """``attn_masks``: the DINO variant's self-attention mask over the queries (denoising groups must not see each
         other; deformable_transformer_dino.py:407-412).  The non-DINO layer (deformable_transformer.py:398-401) is
-        the same call with ``attn_masks=None``."""
+        the same call with ``attn_masks=None``.  ``projected_value`` (keyword-only, new): this layer's
+        ``cross_attn.value_proj(src)`` computed outside, batched over all decoder layers (``batched_value_proj``)."""
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
         sa = self.self_attn(qk, qk, tgt.transpose(0, 1), attn_mask=attn_masks)[0].transpose(0, 1)
         tgt = add_layer_norm(tgt, self.dropout2(sa), self.norm2)
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes, level_start_index,
-                             src_padding_mask)
+                             src_padding_mask, projected_value=projected_value)
         tgt = add_layer_norm(tgt, self.dropout1(ca), self.norm1)
         ffn = _ffn(tgt, self.linear1, self.activation_name, self.dropout3, self.linear2)
         return add_layer_norm(tgt, self.dropout4(ffn), self.norm3)
@@ -158,6 +159,7 @@ class DeformableStack(nn.Module):
         boxes = self.reference_boxes[None].expand(n, -1, -1)                              # [N, Q, 4] (cx, cy, w, h)
         ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
         out = tgt
-        for layer in self.decoder:
-            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None)
+        values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)   # memory is loop-invariant
+        for layer, val in zip(self.decoder, values):
+            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None, projected_value=val)
         return out

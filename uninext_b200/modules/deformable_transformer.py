@@ -15,7 +15,22 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .deformable_layers import fp32_under_autocast
+from .deformable_layers import DeformableTransformerDecoderLayer, fp32_under_autocast
+from .ms_deform_attn import batched_value_proj
+
+
+def inverse_sigmoid(x, eps: float = 1e-5):
+    """logit with both arguments of the log clamped at eps (uninext/util/misc.py:493-497)."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def _projected_values(layers, src, src_padding_mask):
+    """One batched value projection for all layers over the loop-invariant encoder memory, when
+    every layer is this repo's decoder layer; None otherwise (each layer then projects for itself)."""
+    if all(isinstance(l, DeformableTransformerDecoderLayer) for l in layers) and src.is_cuda and len(layers) > 1:
+        return batched_value_proj([l.cross_attn for l in layers], src, src_padding_mask)
+    return None
 
 
 class MLP(nn.Module):
@@ -142,7 +157,66 @@ class DeformableReidHead(nn.Module):
         ref_in = reference_points[:, :, None] * torch.cat((src_valid_ratios, src_valid_ratios), -1)[:, None]
         query_pos = self.ref_point_head(get_sine_pos_embed(ref_in[:, :, 0, :]))      # the same for every layer
         output = tgt
-        for layer in self.layers:
+        values = _projected_values(self.layers, src, src_padding_mask)
+        for i, layer in enumerate(self.layers):
+            kw = {} if values is None else {"projected_value": values[i]}
             output = layer(output, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index,
-                           src_padding_mask, attn_masks)
+                           src_padding_mask, attn_masks, **kw)
         return output
+
+
+class DeformableTransformerDecoder(nn.Module):
+    """The DINO-style decoder loop around the decoder layers (deformable_transformer_dino.py:429-501): per layer the
+    reference boxes are scaled by the valid ratios, turned into a sine embedding -> ``ref_point_head`` -> query_pos, the
+    layer runs, and (when ``bbox_embed`` is attached by the detector, as the reference does) the boxes are refined and
+    detached for the next layer.  ``src`` never changes inside the loop, so all layers' ``value_proj(src)`` run as one
+    batched GEMM up front."""
+
+    def __init__(self, embed_dim, decoder_layer, num_layers, return_intermediate=False, look_forward_twice=False,
+                 use_checkpoint=False):
+        super().__init__()
+        self.layers = nn.ModuleList(copy.deepcopy(decoder_layer) for _ in range(num_layers))
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.look_forward_twice = look_forward_twice
+        self.use_checkpoint = use_checkpoint
+        if use_checkpoint:
+            raise ValueError("activation checkpointing is not supported by this decoder")
+        self.ref_point_head = MLP(2 * embed_dim, embed_dim, embed_dim, 2)
+        self.bbox_embed = None              # attached by the detector (iterative box refinement), like the reference
+        self.class_embed = None
+        self.op_dtype = getattr(decoder_layer, "op_dtype", None)
+
+    @fp32_under_autocast
+    def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
+                query_pos=None, src_padding_mask=None, attn_masks=None):
+        output = tgt
+        bs = output.shape[0]
+        if reference_points.dim() == 2:
+            reference_points = reference_points.unsqueeze(0).repeat(bs, 1, 1)
+        values = _projected_values(self.layers, src, src_padding_mask)
+        intermediate, intermediate_refs = [], []
+        for lid, layer in enumerate(self.layers):
+            if reference_points.shape[-1] == 4:
+                ref_in = reference_points[:, :, None] * torch.cat((src_valid_ratios, src_valid_ratios), -1)[:, None]
+            else:
+                assert reference_points.shape[-1] == 2
+                ref_in = reference_points[:, :, None] * src_valid_ratios[:, None]
+            query_pos = self.ref_point_head(get_sine_pos_embed(ref_in[:, :, 0, :]))
+            kw = {} if values is None else {"projected_value": values[lid]}
+            output = layer(output, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask,
+                           attn_masks, **kw)
+            if self.bbox_embed is not None:                                   # iterative box refinement
+                tmp = self.bbox_embed[lid](output)
+                if reference_points.shape[-1] == 4:
+                    new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()
+                else:
+                    new_ref = torch.cat((tmp[..., :2] + inverse_sigmoid(reference_points), tmp[..., 2:]), -1).sigmoid()
+                reference_points = new_ref.detach()
+            if self.return_intermediate:
+                intermediate.append(output)
+                intermediate_refs.append(new_ref if (self.look_forward_twice and self.bbox_embed is not None)
+                                         else reference_points)
+        if self.return_intermediate:
+            return torch.stack(intermediate), torch.stack(intermediate_refs)
+        return output, reference_points

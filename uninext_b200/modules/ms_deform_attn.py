@@ -102,16 +102,19 @@ class MSDeformAttn(nn.Module):
         raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
 
     def _forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                 input_padding_mask):
+                 input_padding_mask, projected_value=None):
         n, lq, _ = query.shape
         s = input_flatten.shape[1]
         m, l, p = self.n_heads, self.n_levels, self.n_points
         check_levels(input_spatial_shapes, input_level_start_index, s)
         fused = (self.fused and query.is_cuda and query.dtype == torch.float32 and l * p <= 32
                  and not reference_points.requires_grad)
-        value = linear_colsum(input_flatten, self.value_proj, gemm=self.gemm) if fused else self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        if projected_value is not None:        # value_proj (+ padding mask) already applied, e.g. batched over decoder layers
+            value = projected_value
+        else:
+            value = linear_colsum(input_flatten, self.value_proj, gemm=self.gemm) if fused else self.value_proj(input_flatten)
+            if input_padding_mask is not None:
+                value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(n, s, m, self.d_model // m)
         if fused:
             loc, weights = sampling_prologue(query, self.sampling_offsets, self.attention_weights, reference_points,
@@ -129,13 +132,32 @@ class MSDeformAttn(nn.Module):
         return linear_colsum(out, self.output_proj, gemm=self.gemm) if fused else self.output_proj(out)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
-        """query [N,Lq,C]; reference_points [N,Lq,L,2|4]; input_flatten [N,S,C]; returns [N,Lq,C]."""
+                input_padding_mask=None, *, projected_value=None):
+        """query [N,Lq,C]; reference_points [N,Lq,L,2|4]; input_flatten [N,S,C]; returns [N,Lq,C].
+        ``projected_value`` (keyword-only, beyond the reference): ``value_proj(input_flatten)`` with the padding mask
+        already applied, [N,S,C] -- see ``batched_value_proj``."""
         if self.op_dtype is None and torch.is_autocast_enabled():
             # reference: @custom_fwd(cast_inputs=float32) on forward (ms_deform_attn.py:78)
             with torch.autocast("cuda", enabled=False):
-                f = lambda t: t.float() if t.is_floating_point() else t
+                f = lambda t: t.float() if t is not None and t.is_floating_point() else t
                 return self._forward(f(query), f(reference_points), f(input_flatten), input_spatial_shapes,
-                                     input_level_start_index, input_padding_mask)
+                                     input_level_start_index, input_padding_mask, f(projected_value))
         return self._forward(query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                             input_padding_mask)
+                             input_padding_mask, projected_value)
+
+
+def batched_value_proj(attn_modules, input_flatten, input_padding_mask=None):
+    """``[m.value_proj(input_flatten) for m in attn_modules]`` with the padding mask applied, as ONE batched GEMM.
+    The decoder's layers (and the ReID head's) all project the SAME encoder memory (deformable_transformer_dino.py:451-475:
+    ``src`` is loop-invariant), so the six [256 -> 256] projections of 44 646 tokens become one [256 -> 6 x 256] launch,
+    one bias epilogue and one mask pass instead of six of each.  Returns a list of [N, S, C] tensors (views of one
+    [L, N*S, C] buffer), to be passed as ``projected_value=``."""
+    from uninext_b200.functions.fused import batched_linear
+    mods = list(attn_modules)
+    n, s, c = input_flatten.shape
+    w = torch.stack([m.value_proj.weight for m in mods])
+    b = torch.stack([m.value_proj.bias for m in mods])
+    y = batched_linear(input_flatten.reshape(n * s, c), w, b)                     # [L, N*S, C]
+    if input_padding_mask is not None:
+        y = y.masked_fill(input_padding_mask.reshape(1, n * s, 1), 0.0)
+    return [y[i].view(n, s, -1) for i in range(len(mods))]
