@@ -67,12 +67,19 @@ uint64_t msda_launch_count(void);
  *                           kernels (the measured-faster default)
  *   MSDA_KNOB_BWD_WIN_ROWS  shared-memory window of the slab backward in rows of 128 B (-1 = all that fits)
  *   MSDA_KNOB_BWD_LIST_CAP  entries per row-class list of the slab backward (even, >= 8)
- *   MSDA_KNOB_FWD_SLAB_CTAS resident CTAs per SM of the slab forward (1 or 2) */
+ *   MSDA_KNOB_FWD_SLAB_CTAS resident CTAs per SM of the slab forward (1 or 2)
+ *   MSDA_KNOB_F32_VEC8_FWD / _BWD   lane shape of the fp32 tiled kernels: 1 = 4 lanes x 32 B per row, 0 = 8 lanes x 16 B
+ *   MSDA_KNOB_BF16_FINE_ROWS        msda_backward_bf16 with a bf16 result: levels of at least this many rows accumulate
+ *                                   grad_value directly in bf16 (packed 8-byte reds); the others in fp32.  0 = all fp32.
+ *                                   (The only knob that changes results: within the 1e-2 bf16 tolerance, see DESIGN.md.) */
 #define MSDA_KNOB_SLAB          0
 #define MSDA_KNOB_BWD_WIN_ROWS  1
 #define MSDA_KNOB_BWD_LIST_CAP  2
 #define MSDA_KNOB_FWD_SLAB_CTAS 3
-#define MSDA_KNOB_COUNT         4
+#define MSDA_KNOB_F32_VEC8_FWD  4   /* fp32 tiled forward: 8 channels per lane (LDG.256), D in {32, 64}; 0 / 1        */
+#define MSDA_KNOB_F32_VEC8_BWD  5   /* fp32 tiled backward: same lane shape; 0 / 1                                     */
+#define MSDA_KNOB_BF16_FINE_ROWS 6  /* bf16 backward: levels with H*W >= this accumulate grad_value in bf16; 0 = off */
+#define MSDA_KNOB_COUNT         7
 #define MSDA_KNOB_QUERY         (-1000000)
 int msda_set_knob(int knob, int value);
 
@@ -102,7 +109,9 @@ int msda_backward_f64(const double *grad_out, const double *value,
                       int N, int S, int M, int D, int L, int Lq, int P,
                       double *grad_value, double *grad_sampling_loc, double *grad_attn_weight, void *stream);
 /* bf16 backward accumulates grad_value in fp32: `grad_value_f32` [N,S,M,D] fp32 is the accumulator (zero-filled by
- * the callee) and `grad_value` receives its bf16 rounding. Pass grad_value == NULL to keep only the fp32 result. */
+ * the callee) and `grad_value` receives its bf16 rounding. Pass grad_value == NULL to keep only the fp32 result.
+ * With MSDA_KNOB_BF16_FINE_ROWS > 0 and grad_value != NULL the big ("fine") levels are accumulated directly in
+ * `grad_value` and only the rows of the coarse levels of `grad_value_f32` are used (as scratch). */
 int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value,
                        const int64_t *spatial_shapes, const int64_t *level_start_index,
                        const float *sampling_loc, const float *attn_weight,

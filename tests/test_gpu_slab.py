@@ -1,8 +1,8 @@
-"""GPU tests (-m gpu) of the slab-ordered kernels (uninext_b200/csrc/msda_slab.cuh): LDG.256 forward and the backward
-that accumulates the coarse levels of grad_value in a shared-memory window.  At BASELINE sizes they are selected
-automatically (and are what tests/test_gpu_parity.py's full-size cases exercise); here `msda_set_knob` forces them
-onto small and ragged problems so that every branch -- window level sets, list overflow falling back to red.global,
-partial tiles, CTAs spanning several slabs -- is compared with the fp64 oracle and with the tiled kernels.
+"""GPU tests (-m gpu) of the kernel families selected by `msda_set_knob`: the slab-ordered kernels
+(uninext_b200/csrc/msda_slab.cuh: LDG.256 forward, backward with a shared-memory window for the coarse levels of
+grad_value) and the 32-byte lane shape of the fp32 tiled kernels.  The knobs force them onto small and ragged problems
+so that every branch -- window level sets, list overflow falling back to red.global, partial tiles, CTAs spanning
+several slabs -- is compared with the fp64 oracle and with the default tiled kernels.
 
 The slab kernels are an OPT-IN family (MSDA_KNOB_SLAB=1): measured on B200 they cut L2 traffic (forward: -48 % L2 sectors,
 L1 hit rate 34 % -> 65 %; backward: -43 % red sectors) but not run time, because the SM's load/store data pipe, not
@@ -28,7 +28,7 @@ DEV = "cuda"
 @pytest.fixture
 def knobs():
     lib = _cabi.load()
-    saved = [lib.msda_set_knob(k, -1000000) for k in range(4)]
+    saved = [lib.msda_set_knob(k, -1000000) for k in range(7)]
     yield lib
     for k, v in enumerate(saved):
         lib.msda_set_knob(k, v)
@@ -142,3 +142,40 @@ def test_slab_and_tiled_kernels_agree_at_cfg2(knobs):
     for i, (a, b) in enumerate(zip(got, ref)):
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 2e-5 * scale, i
+
+
+@pytest.mark.parametrize("kind", ["enc", "dec"])
+def test_f32_vec8_lane_shape_vs_oracle(knobs, kind):
+    """fp32 tiled kernels with 4 lanes x 32 B per row (LDG.256) instead of 8 lanes x 16 B."""
+    knobs.msda_set_knob(_cabi.KNOB_F32_VEC8_FWD, 1)
+    knobs.msda_set_knob(_cabi.KNOB_F32_VEC8_BWD, 1)
+    _check(make_inputs(CONFIGS["cfg1"], kind, DEV, seed=29, wild_fraction=0.1), 1e-4)
+
+
+@pytest.mark.parametrize("D", [32, 64])
+def test_f32_vec8_ragged_vs_oracle(knobs, D):
+    knobs.msda_set_knob(_cabi.KNOB_F32_VEC8_FWD, 1)
+    knobs.msda_set_knob(_cabi.KNOB_F32_VEC8_BWD, 1)
+    g = torch.Generator().manual_seed(31)
+    ss = torch.as_tensor([(5, 6), (3, 3)], dtype=torch.long)
+    lsi = torch.as_tensor([0, 30])
+    N, M, Lq, L, P = 3, 5, 13, 2, 3
+    inp = dict(value=torch.randn(N, 39, M, D, generator=g).to(DEV), spatial_shapes=ss.to(DEV), level_start_index=lsi.to(DEV),
+               sampling_locations=(torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3).to(DEV),
+               attention_weights=torch.rand(N, Lq, M, L, P, generator=g).to(DEV),
+               grad_output=torch.randn(N, Lq, M * D, generator=g).to(DEV))
+    _check(inp, 1e-4)
+
+
+# cfg1 levels have 1600 / 400 / 100 / 25 rows: threshold 1 = every level accumulates in bf16, 500 = the finest only,
+# 5000 = none (all fp32, but through the mixed code path).
+@pytest.mark.parametrize("fine_rows", [1, 500, 5000])
+def test_bf16_backward_mixed_accumulation_vs_oracle(knobs, fine_rows):
+    """bf16 backward with the big levels' grad_value accumulated directly in the bf16 result (packed reds) and the small
+    levels in fp32 scratch rows: every output within the bf16 tolerance of the fp64 oracle."""
+    knobs.msda_set_knob(_cabi.KNOB_BF16_FINE_ROWS, fine_rows)
+    inp = make_inputs(CONFIGS["cfg1"], "enc", DEV, dtype=torch.bfloat16, seed=37, wild_fraction=0.1)
+    before = knobs.msda_launch_count()
+    out, gv, gl, ga = _check(inp, 1e-2)
+    assert gv.dtype == torch.bfloat16
+    assert knobs.msda_launch_count() - before == 4          # forward, zero coarse scratch rows, backward, round coarse rows

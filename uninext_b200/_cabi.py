@@ -36,7 +36,8 @@ SIGNATURES = {
     "msda_linear_tf32": (_i, [_vp] * 3 + [ctypes.c_int64, _i, _i, _vp, _vp]),
 }
 ABI_VERSION = 1
-KNOB_SLAB, KNOB_BWD_WIN_ROWS, KNOB_BWD_LIST_CAP, KNOB_FWD_SLAB_CTAS = 0, 1, 2, 3      # include/msda_b200.h
+(KNOB_SLAB, KNOB_BWD_WIN_ROWS, KNOB_BWD_LIST_CAP, KNOB_FWD_SLAB_CTAS, KNOB_F32_VEC8_FWD, KNOB_F32_VEC8_BWD,
+ KNOB_BF16_FINE_ROWS) = range(7)                                                      # include/msda_b200.h
 
 _lib = None
 

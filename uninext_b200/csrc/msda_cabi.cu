@@ -62,6 +62,9 @@ struct Knobs {
         v[MSDA_KNOB_BWD_WIN_ROWS].store(env_int("MSDA_BWD_WIN_ROWS", -1));
         v[MSDA_KNOB_BWD_LIST_CAP].store(env_int("MSDA_BWD_LIST_CAP", 48));
         v[MSDA_KNOB_FWD_SLAB_CTAS].store(env_int("MSDA_FWD_SLAB_CTAS", 2));
+        v[MSDA_KNOB_F32_VEC8_FWD].store(env_int("MSDA_F32_VEC8_FWD", 0));
+        v[MSDA_KNOB_F32_VEC8_BWD].store(env_int("MSDA_F32_VEC8_BWD", 0));
+        v[MSDA_KNOB_BF16_FINE_ROWS].store(env_int("MSDA_BF16_FINE_ROWS", 0));
     }
 };
 Knobs &knobs() { static Knobs k; return k; }
@@ -136,10 +139,9 @@ constexpr int kFwdMinCtas = 4, kBwdMinCtas = 2;     // r01d sweep: fwd flat for 
 template <typename T> struct FwdVec { static constexpr int v = 16 / sizeof(T); };      // 16-byte row slices
 template <typename T> struct BwdVec { static constexpr int v = 4; };                  // 4 channels per lane (see RowVec)
 
-template <typename T, int D, int LP_MAX>
+template <typename T, int D, int LP_MAX, int VEC = FwdVec<T>::v>
 cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                        const Dims &d, T *out, cudaStream_t st) {
-    constexpr int VEC = FwdVec<T>::v;
     constexpr int GPW = 32 / (D / VEC);
     constexpr bool kCanStage = (LP_MAX <= 16);          // per-warp double buffer must fit static shared memory
     constexpr bool kCanSplit = (LP_MAX % GPW == 0) && (LP_MAX / GPW <= D / VEC);
@@ -162,10 +164,9 @@ cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi
     return cudaGetLastError();
 }
 
-template <typename T, int D, int LP_MAX>
+template <typename T, int D, int LP_MAX, int VEC = BwdVec<T>::v>
 cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                        const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
-    constexpr int VEC = BwdVec<T>::v;
     constexpr int GPW = 32 / (D / VEC);
     constexpr bool kCanStage = (LP_MAX <= 16);
     constexpr bool kCanSplit = (LP_MAX % GPW == 0) && (LP_MAX / GPW <= D / VEC);
@@ -183,7 +184,7 @@ cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes,
     const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
     kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
-                                               npairs, allow_patches(), gv, gl, ga);
+                                               npairs, allow_patches(), gv, gl, ga, nullptr, 0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -254,6 +255,29 @@ cudaError_t launch_bwd_slab(const T *grad_out, const T *value, const int64_t *sh
     return cudaGetLastError();
 }
 
+// bf16 backward with the fine levels accumulated in the bf16 result (msda_bwd_tiled MIXED): D = 32, L*P <= 16, large launches.
+cudaError_t launch_bwd_mixed(const __nv_bfloat16 *go, const __nv_bfloat16 *value, const int64_t *shapes, const int64_t *lsi,
+                             const float *loc, const float *attn, const Dims &d, float *scratch, __nv_bfloat16 *gv16,
+                             float *gl, float *ga, int fine_min_rows, cudaStream_t st) {
+    using T = __nv_bfloat16;
+    constexpr int VEC = 4, DD = 32, LP_MAX = 16;
+    constexpr int GPW = 32 / (DD / VEC);
+    const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
+    const bool tma = use_tma_staging(d);
+    static std::atomic<int> c_tma[kMaxDevices], c_ldg[kMaxDevices];
+    auto k_tma = msda::msda_bwd_tiled<T, VEC, DD, LP_MAX, kBwdMinCtas, true, false, true>;
+    auto k_ldg = msda::msda_bwd_tiled<T, VEC, DD, LP_MAX, kBwdMinCtas, false, false, true>;
+    const int slots = tma ? resident_ctas_cached(k_tma, c_tma) : resident_ctas_cached(k_ldg, c_ldg);
+    const unsigned iter_pairs = msda::kTiledWarps * GPW;
+    const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;
+    const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
+    (tma ? k_tma : k_ldg)<<<grid, msda::kTiledThreads, 0, st>>>(go, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq,
+                                                                 d.P, npairs, allow_patches(), scratch, gl, ga, gv16,
+                                                                 fine_min_rows);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 #define MSDA_ROUTE_LP(T, DD, CALL)                                   \
     (LP <= 16 ? CALL<T, DD, 16> : CALL<T, DD, 32>)
 
@@ -263,6 +287,12 @@ cudaError_t fwd_fast(const T *value, const int64_t *shapes, const int64_t *lsi, 
     const int LP = d.L * d.P;
     if (use_slab(d, (unsigned)((long long)d.N * d.Lq * d.M), value, out))
         return launch_fwd_slab<T>(value, shapes, lsi, loc, attn, d, out, st);
+    if constexpr (sizeof(T) == 4) {           // fp32, 32-byte lanes (LDG.256): needs 32-byte aligned rows
+        if (knob(MSDA_KNOB_F32_VEC8_FWD) == 1 && LP <= 16 && (d.D == 32 || d.D == 64) &&
+            !(reinterpret_cast<uintptr_t>(value) & 31u))
+            return d.D == 32 ? launch_fwd<T, 32, 16, 8>(value, shapes, lsi, loc, attn, d, out, st)
+                             : launch_fwd<T, 64, 16, 8>(value, shapes, lsi, loc, attn, d, out, st);
+    }
     switch (d.D) {
         case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st); break;
         case 32: return MSDA_ROUTE_LP(T, 32, launch_fwd)(value, shapes, lsi, loc, attn, d, out, st);
@@ -277,6 +307,11 @@ cudaError_t bwd_fast(const T *go, const T *value, const int64_t *shapes, const i
     const int LP = d.L * d.P;
     if (use_slab(d, (unsigned)((long long)d.N * d.Lq * d.M), value, gv))
         return launch_bwd_slab<T>(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
+    if constexpr (sizeof(T) == 4) {
+        if (knob(MSDA_KNOB_F32_VEC8_BWD) == 1 && LP <= 16 && d.D == 32 &&
+            !((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(go)) & 31u))
+            return launch_bwd<T, 32, 16, 8>(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
+    }
     switch (d.D) {
         case 16: if constexpr (sizeof(T) == 4) return MSDA_ROUTE_LP(T, 16, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st); break;
         case 32: return MSDA_ROUTE_LP(T, 32, launch_bwd)(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
@@ -434,10 +469,30 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t nval = (size_t)N * S * M * D;
-    cudaError_t err = cudaMemsetAsync(grad_value_f32, 0, sizeof(float) * nval, st);
-    if (err != cudaSuccess) return (int)err;
     const __nv_bfloat16 *go = reinterpret_cast<const __nv_bfloat16 *>(grad_out);
     const __nv_bfloat16 *v = reinterpret_cast<const __nv_bfloat16 *>(value);
+    const int fine_rows = knob(MSDA_KNOB_BF16_FINE_ROWS);
+    if (fine_rows > 0 && grad_value != nullptr && al && use_fast(2, d) && D == 32 && L * P <= 16 &&
+        !use_split((unsigned)((long long)N * Lq * M)) && !(reinterpret_cast<uintptr_t>(grad_value) & 15u)) {
+        // mixed accumulation: bf16 result zero-filled (fine levels add into it), fp32 scratch zero-filled for the coarse
+        // levels only, one rounding pass over the coarse rows at the end -- no full-size fp32 round trip
+        __nv_bfloat16 *gv16 = reinterpret_cast<__nv_bfloat16 *>(grad_value);
+        cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(uint16_t) * nval, st);
+        if (e != cudaSuccess) return (int)e;
+        const dim3 hgrid((unsigned)(num_sms() * 2 / (N < 1 ? 1 : N) + 1), (unsigned)N);
+        msda::msda_coarse_rows<false><<<hgrid, 256, 0, st>>>(grad_value_f32, gv16, spatial_shapes, level_start_index, L, S,
+                                                             M * D, fine_rows);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = launch_bwd_mixed(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d, grad_value_f32, gv16,
+                             grad_sampling_loc, grad_attn_weight, fine_rows, st);
+        if (e != cudaSuccess) return (int)e;
+        msda::msda_coarse_rows<true><<<hgrid, 256, 0, st>>>(grad_value_f32, gv16, spatial_shapes, level_start_index, L, S,
+                                                            M * D, fine_rows);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return (int)cudaGetLastError();
+    }
+    cudaError_t err = cudaMemsetAsync(grad_value_f32, 0, sizeof(float) * nval, st);
+    if (err != cudaSuccess) return (int)err;
     if (al && use_fast(2, d))
         err = bwd_fast<__nv_bfloat16>(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                       grad_value_f32, grad_sampling_loc, grad_attn_weight, st);

@@ -69,6 +69,21 @@ template <> struct RowVec<float, 4> {
     }
 };
 
+// fp32, 8 channels per lane: one 32-byte access (sm_100 LDG.256 / STG.256 would need 32-byte alignment of the tensor, which
+// the router checks).  4 lanes cover a 128-byte row, 8 rows per warp instruction: 119 B/clk/SM from L1 against 80 for the
+// 16-byte shape (profiles/r02b_ubench_smem_rmw_and_egress.txt).
+template <> struct RowVec<float, 8> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void load(const float *p, float (&v)[8]) {
+        asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+    }
+    __device__ static __forceinline__ void store(float *p, const float (&v)[8]) {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
 template <> struct RowVec<__nv_bfloat16, 4> {
     static constexpr int kElems = 4;
     __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) {
@@ -108,6 +123,14 @@ template <> struct RowVec<__nv_bfloat16, 8> {
 // Vector reduction into global memory: one 16-byte red per call (sm_90+), no return value.
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 4 bf16 lanes of a grad_value row, added in place (8-byte packed red, round-to-nearest; sm_90+): used by the bf16
+// backward for the FINE levels, whose rows collect few contributions (see msda_bwd_tiled, MIXED).
+__device__ __forceinline__ void red_add_bf16x4(__nv_bfloat16 *addr, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(addr), "r"(*reinterpret_cast<const unsigned *>(&lo)),
+                 "r"(*reinterpret_cast<const unsigned *>(&hi)) : "memory");
 }
 
 }  // namespace msda

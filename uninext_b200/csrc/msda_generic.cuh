@@ -157,4 +157,34 @@ msda_f32_to_bf16(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
         dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// Mixed bf16 backward (msda_bwd_tiled, MIXED): rows of the COARSE levels (H_l * W_l < fine_min_rows) are accumulated in
+// the fp32 scratch and rounded into the bf16 result afterwards; rows of the fine levels never touch the scratch.  Both
+// helpers walk the rows of one batch element per blockIdx.y and read the level table on the device.
+//   ROUND = false: zero the scratch rows of the coarse levels (before the backward kernel);
+//   ROUND = true : dst[row] = bf16(scratch[row]) for the coarse levels (after it).
+template <bool ROUND>
+__global__ void __launch_bounds__(256)
+msda_coarse_rows(float *__restrict__ scratch, __nv_bfloat16 *__restrict__ dst, const int64_t *__restrict__ shapes,
+                 const int64_t *__restrict__ lsi, int L, int S, int row_elems, int fine_min_rows) {
+    const int b = blockIdx.y;
+    const int quads = row_elems / 4;
+    for (int l = 0; l < L; ++l) {
+        const int rows = (int)(shapes[2 * l] * shapes[2 * l + 1]);
+        if (rows >= fine_min_rows) continue;
+        const long long first = ((long long)b * S + (int)lsi[l]) * row_elems;
+        const long long n4 = (long long)rows * quads;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            float4 *p = reinterpret_cast<float4 *>(scratch + first) + i;
+            if (ROUND) {
+                const float4 v = *p;
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                reinterpret_cast<uint2 *>(dst + first)[i] = make_uint2(*reinterpret_cast<const unsigned *>(&lo),
+                                                                      *reinterpret_cast<const unsigned *>(&hi));
+            } else {
+                *p = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+}
+
 }  // namespace msda

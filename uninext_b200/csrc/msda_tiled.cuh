@@ -351,14 +351,21 @@ __device__ __forceinline__ void group_reduce_scatter(float (&part)[LPR][4], int 
 // Per tap only the four corner dot products  dot_k = sum_c g[c] * V_k[c]  cross lanes; the bilinear coefficients are
 // applied afterwards by the single lane that owns the tap.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT>
+// MIXED (bf16 storage only): grad_value of the FINE levels (H_l * W_l >= fine_min_rows: the big maps, whose rows
+// collect a few dozen contributions each) is accumulated directly in the bf16 output with packed 8-byte reds -- half the
+// bytes through the SM's crossbar port, which is what bounds this kernel -- while the coarse levels (hundreds to
+// thousands of contributions per row) keep the fp32 accumulator.  The fine flag travels in bit 31 of the record's row
+// index (rows are < 2^30).
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT, bool MIXED = false>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
                int N, int S, int M, int L, int Lq, int P, unsigned npairs, int allow_patches,
-               float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn)
+               float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
+               __nv_bfloat16 *__restrict__ grad_value_bf16, int fine_min_rows)
 {
+    static_assert(!MIXED || (sizeof(T) == 2 && VEC == 4), "MIXED accumulates bf16 rows with 8-byte packed reds");
     constexpr int LPR = D / VEC;
     constexpr int GPW = 32 / LPR;
     constexpr int PPW = SPLIT ? 1 : GPW;                    // see msda_fwd_tiled
@@ -445,7 +452,8 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                     const int l = s / P;
                     const TapGeom gm = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
                     tw[k] = masked_weights(gm, a);
-                    tr[k] = make_int2(gm.r0, gm.r1 | (gm.dw << 31));
+                    const int fine = (MIXED && wm.H[l] * wm.W[l] >= fine_min_rows) ? (int)0x80000000 : 0;
+                    tr[k] = make_int2(gm.r0 | fine, gm.r1 | (gm.dw << 31));
                     tlh[k] = gm.lh; tlw[k] = gm.lw; ta[k] = a; tmeta[k] = gm.mask | ((unsigned)l << 4);
                 }
             }
@@ -471,8 +479,9 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                     const int2 rr = slab.rows(j);
                     const float w[4] = {w4.x, w4.y, w4.z, w4.w};
                     const unsigned dwo = (rr.y < 0) ? row_elems : 0u;
+                    const bool fine = MIXED && rr.x < 0;
                     unsigned long long off[4];
-                    off[0] = (unsigned long long)(unsigned)rr.x * row_elems;
+                    off[0] = (unsigned long long)(unsigned)(rr.x & 0x7fffffff) * row_elems;
                     off[1] = off[0] + dwo;
                     off[2] = (unsigned long long)(unsigned)(rr.y & 0x7fffffff) * row_elems;
                     off[3] = off[2] + dwo;
@@ -485,6 +494,13 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
                         for (int e = 0; e < VEC; ++e) dsum = fmaf(g[e], v[e], dsum);
                         part[j][c] = dsum;
                         if (w[c] != 0.f) {            // masked-out corners, dead taps and idle groups carry weight 0
+                            if constexpr (MIXED) {
+                                if (fine) {
+                                    red_add_bf16x4(grad_value_bf16 + slab_off + off[c], w[c] * g[0], w[c] * g[1], w[c] * g[2],
+                                                   w[c] * g[3]);
+                                    continue;
+                                }
+                            }
 #pragma unroll
                             for (int e = 0; e < VEC; e += 4)
                                 red_add_v4(gbase + off[c] + e, w[c] * g[e], w[c] * g[e + 1], w[c] * g[e + 2],
