@@ -145,6 +145,28 @@ int msda_layernorm_backward_f32(const float *dy, const float *z, const float *ga
                                 const float *rstd, int64_t rows, int cols, float *dz, float *dgamma, float *dbeta,
                                 void *stream);
 
+/* ---- CondInst dynamic mask head (uninext/models/ddetrs.py:488-598, 895-958) ----------------
+ * msda_condinst_forward_f32: logits[i, y, x] = MLP_i(rel_x, rel_y, feats[b(i), :, y, x]) for every selected instance i --
+ *   the reference's three grouped 1x1 convolutions (groups = #instances, `mask_heads_forward`) over a materialised
+ *   [1, I*10, H, W] input, fused into one pass that materialises nothing.
+ *     feats [N, 8, H, W]; params [I, 169] laid out as parse_dynamic_params expects (w1[8][10] | w2[8][8] | w3[8] | b1 | b2 | b3);
+ *     refs [I, 2] reference points in input-image pixels; inst_start [N + 1] int32 (device): instances of image b are
+ *     [inst_start[b], inst_start[b+1]); max_inst = largest per-image count (host value, sizes the grid);
+ *     stride = mask_feat_stride; rel_coord = 1 prepends (ref - pixel location) as two input channels, 0 feeds zeros;
+ *     logits [I, H, W].
+ * msda_condinst_backward_f32: grad_feats [N, 8, H, W] (fully written), grad_params [I, 169] and grad_refs [I, 2] (zero-filled
+ *   by the callee, then accumulated).
+ * msda_aligned_bilinear_forward/backward_f32: `aligned_bilinear` (ddetrs.py:921-942) on [planes, h, w] -> [planes, f*h, f*w]. */
+int msda_condinst_forward_f32(const float *feats, const float *params, const float *refs, const int32_t *inst_start,
+                              int N, int H, int W, int I, int max_inst, int stride, int rel_coord, float *logits,
+                              void *stream);
+int msda_condinst_backward_f32(const float *grad_logits, const float *feats, const float *params, const float *refs,
+                               const int32_t *inst_start, int N, int H, int W, int I, int stride, int rel_coord,
+                               float *grad_feats, float *grad_params, float *grad_refs, void *stream);
+int msda_aligned_bilinear_forward_f32(const float *in, int64_t planes, int h, int w, int factor, float *out, void *stream);
+int msda_aligned_bilinear_backward_f32(const float *grad_out, int64_t planes, int h, int w, int factor, float *grad_in,
+                                       void *stream);
+
 /* ---- tcgen05 GEMM for the Linears that bracket the op:  C[M,N] = A[M,K] . W[N,K]^T + bias[N]  (fp32 storage, TF32 MMA
  * with fp32 accumulation in tensor memory; TMA-fed).  K % 32 == 0, N % 32 == 0 (N % 64 == 0 above 256), N <= 512.
  * Replaces torch.nn.functional.linear for value_proj / output_proj / the concatenated sampling projection

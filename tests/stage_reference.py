@@ -13,6 +13,7 @@ gpurun snapshot), and nothing under ``uninext_b200/`` imports them. What is copi
     ops/functions/{__init__,ms_deform_attn_func}.py       (a1/a2: the autograd boundary)
     ops/modules/{__init__,ms_deform_attn}.py              (a9)
     deformable_transformer.py, deformable_transformer_dino.py   (a10/a11/a12 + reference-point helpers, f-3)
+    ../ddetrs.py                                          (f-4: dynamic_mask_with_coords, aligned_bilinear, ...)
 
 What is WRITTEN here (not copied) so those files import without the rest of UNINEXT: four stub modules for imports
 that are off the hot path -- ``util/misc.py`` (``inverse_sigmoid`` only), ``vlfusion.py`` / ``fuse_helper.py`` (the
@@ -36,17 +37,29 @@ COPIES = [
     "ops/modules/ms_deform_attn.py",
     "deformable_transformer.py",
     "deformable_transformer_dino.py",
+    "../ddetrs.py",                                        # CondInst dynamic mask head (f-4)
 ]
 
 STUBS = {
     "__init__.py": "",
     "util/__init__.py": "",
     "util/misc.py": (
-        '"""Stub written by tests/stage_reference.py: the one helper the transformer files import from util/misc.py."""\n'
+        '"""Stub written by tests/stage_reference.py: the helpers the staged files import from util/misc.py."""\n'
         "import torch\n\n\n"
         "def inverse_sigmoid(x, eps=1e-5):\n"
         "    x = x.clamp(min=0, max=1)\n"
-        "    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))\n"),
+        "    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))\n\n\n"
+        "class NestedTensor:\n    pass\n\n\n"
+        "def interpolate(*a, **k):\n    return torch.nn.functional.interpolate(*a, **k)\n\n\n"
+        "def nested_tensor_from_tensor_list(*a, **k):\n    raise NotImplementedError\n"),
+    "models/conv_with_kaiming_uniform.py": (
+        '"""Stub written by tests/stage_reference.py (mask-feature convolutions are off the hot path)."""\n\n\n'
+        "def conv_with_kaiming_uniform(*a, **k):\n    raise NotImplementedError\n"),
+    "../detectron2/__init__.py": '"""Stub package written by tests/stage_reference.py: names ddetrs.py imports at module level."""\n',
+    "../detectron2/structures.py": "class Instances:\n    pass\n",
+    "../detectron2/data/__init__.py": "",
+    "../detectron2/data/datasets/__init__.py": "",
+    "../detectron2/data/datasets/builtin_meta.py": "COCO_CATEGORIES = []\n",
     "models/__init__.py": "",
     "models/deformable_detr/__init__.py": "",
     "models/deformable_detr/ops/__init__.py": "",
@@ -103,6 +116,16 @@ def import_reference():
         return tuple(importlib.import_module(f"{base}.{m}") for m in
                      ("ops.functions.ms_deform_attn_func", "ops.modules.ms_deform_attn", "deformable_transformer",
                       "deformable_transformer_dino"))
+
+
+def import_ddetrs():
+    """The staged uninext/models/ddetrs.py (CondInst mask branch) with its off-path imports stubbed."""
+    import importlib
+    import warnings
+    import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return importlib.import_module("uninext_ref.models.ddetrs")
 
 
 if __name__ == "__main__":

@@ -133,4 +133,20 @@ __device__ __forceinline__ void red_add_bf16x4(__nv_bfloat16 *addr, float a, flo
                  "r"(*reinterpret_cast<const unsigned *>(&hi)) : "memory");
 }
 
+// One corner of the MIXED bf16 backward without control flow: exactly one of the two reds executes (or none when the
+// corner weight is zero).  Straight-line predicated code keeps the four row loads of a tap ahead of the reds; an
+// if / else around two different red instructions made ptxas serialise load -> branch -> red per corner (+45 % run time).
+__device__ __forceinline__ void red_add_mixed(bool to_bf16, __nv_bfloat16 *a16, bool to_f32, float *a32, float a, float b,
+                                              float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    asm volatile(
+        "{\n\t.reg .pred p16, p32;\n\t"
+        "setp.ne.b32 p16, %0, 0;\n\t"
+        "setp.ne.b32 p32, %1, 0;\n\t"
+        "@p16 red.global.add.noftz.v2.bf16x2 [%2], {%3, %4};\n\t"
+        "@p32 red.global.add.v4.f32 [%5], {%6, %7, %8, %9};\n\t}"
+        ::"r"((unsigned)to_bf16), "r"((unsigned)to_f32), "l"(a16), "r"(*reinterpret_cast<const unsigned *>(&lo)),
+          "r"(*reinterpret_cast<const unsigned *>(&hi)), "l"(a32), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace msda

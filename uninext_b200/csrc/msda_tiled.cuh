@@ -493,14 +493,11 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) dsum = fmaf(g[e], v[e], dsum);
                         part[j][c] = dsum;
-                        if (w[c] != 0.f) {            // masked-out corners, dead taps and idle groups carry weight 0
-                            if constexpr (MIXED) {
-                                if (fine) {
-                                    red_add_bf16x4(grad_value_bf16 + slab_off + off[c], w[c] * g[0], w[c] * g[1], w[c] * g[2],
-                                                   w[c] * g[3]);
-                                    continue;
-                                }
-                            }
+                        if constexpr (MIXED) {        // predicated, branch-free: bf16 result row or fp32 scratch row
+                            const bool nz = w[c] != 0.f;
+                            red_add_mixed(nz && fine, grad_value_bf16 + slab_off + off[c], nz && !fine, gbase + off[c],
+                                          w[c] * g[0], w[c] * g[1], w[c] * g[2], w[c] * g[3]);
+                        } else if (w[c] != 0.f) {     // masked-out corners, dead taps and idle groups carry weight 0
 #pragma unroll
                             for (int e = 0; e < VEC; e += 4)
                                 red_add_v4(gbase + off[c] + e, w[c] * g[e], w[c] * g[e + 1], w[c] * g[e + 2],
