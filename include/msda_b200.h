@@ -172,6 +172,13 @@ int msda_aligned_bilinear_backward_f32(const float *grad_out, int64_t planes, in
  * Replaces torch.nn.functional.linear for value_proj / output_proj / the concatenated sampling projection
  * (ops/modules/ms_deform_attn.py:95,99-100,115) when TF32 GEMMs are allowed. bias may be NULL. */
 int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t M, int N, int K, float *C, void *stream);
+/* W-stationary variant with a fused tail, for K <= 256 and N <= 256 (N % 64 == 0; msda_linear_tf32_ws_ok tells):
+ *   C = A . W^T + bias;  rows with row_mask[m] != 0 are written as zeros (the `masked_fill(input_padding_mask)` that follows
+ *   value_proj, ops/modules/ms_deform_attn.py:96-97);  relu != 0 applies max(., 0) (FFN linear1).  bias / row_mask may be NULL.
+ *   msda_linear_tf32 itself routes eligible shapes to this kernel. */
+int msda_linear_tf32_ex(const float *A, const float *W, const float *bias, const uint8_t *row_mask, int64_t M, int N, int K,
+                        int relu, float *C, void *stream);
+int msda_linear_tf32_ws_ok(int N, int K);
 
 #ifdef __cplusplus
 }

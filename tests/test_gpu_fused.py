@@ -202,3 +202,57 @@ def test_fused_and_unfused_module_agree():
     assert _rel(outs[0][0], outs[1][0]) < 1e-4 and _rel(outs[0][1], outs[1][1]) < 1e-3
     for k in outs[0][2]:
         assert _rel(outs[0][2][k], outs[1][2][k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("m,n,k,use_mask,relu", [(128, 256, 256, False, False), (300, 256, 256, True, False), (1, 64, 32, False, True),
+                                                   (1000, 192, 128, True, True), (44646, 256, 256, True, False)])
+def test_tcgen05_w_stationary_linear_with_fused_tail(m, n, k, use_mask, relu):
+    """msda_linear_tf32_ex: C = A W^T + bias with the padding-mask zeroing (ms_deform_attn.py:96-97) and ReLU in the epilogue."""
+    from uninext_b200.functions.fused import tcgen05_linear_ex, tcgen05_ws_ok
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.randn(m, k, generator=g).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.1).to(DEV)
+    b = torch.randn(n, generator=g).to(DEV)
+    mask = (torch.rand(m, generator=g) < 0.3).to(DEV) if use_mask else None
+    assert tcgen05_ws_ok(a, w)
+    got = tcgen05_linear_ex(a, w, b, mask, relu)
+    want = a.double() @ w.double().t() + b.double()
+    if relu:
+        want = want.clamp_min(0)
+    if mask is not None:
+        want = want.masked_fill(mask[:, None], 0.0)
+        assert (got[mask] == 0).all()                      # masked rows are exact zeros, not small numbers
+    assert _rel(got, want) < 2e-3                            # TF32 products, fp32 accumulation
+
+
+def test_module_auto_gemm_follows_allow_tf32():
+    """gemm="auto" (the default): cuBLAS fp32 unless the caller allowed TF32; then value_proj runs on the W-stationary
+    tcgen05 kernel with its padding mask fused (no masked_fill launch) and stays within TF32 distance of the fp32 result."""
+    from uninext_b200 import _cabi
+    from uninext_b200.workloads import CONFIGS, level_tensors
+    from uninext_b200.modules.deformable_layers import encoder_reference_points
+    cfg = CONFIGS["cfg1"]
+    ss, lsi = level_tensors(cfg.shapes, DEV)
+    torch.manual_seed(9)
+    mod = MSDeformAttn().to(DEV)
+    assert mod.gemm == "auto"
+    src = torch.randn(2, cfg.S, 256, device=DEV)
+    ref = encoder_reference_points(cfg.shapes, torch.ones(2, 4, 2, device=DEV), DEV)
+    mask = torch.zeros(2, cfg.S, dtype=torch.bool, device=DEV); mask[1, -200:] = True
+    lib = _cabi.load()
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        n0 = lib.msda_launch_count()
+        want = mod(src, ref, src, ss, lsi, mask)
+        strict = lib.msda_launch_count() - n0
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n0 = lib.msda_launch_count()
+        x = src.clone().requires_grad_(True)
+        got = mod(x, ref, x, ss, lsi, mask)
+        assert lib.msda_launch_count() - n0 == strict            # launch counter counts msda_cabi kernels only (GEMMs separately)
+        got.square().mean().backward()
+        assert torch.isfinite(x.grad).all()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert _rel(got, want) < 1e-2

@@ -34,6 +34,8 @@ SIGNATURES = {
     "msda_add_layernorm_forward_f32": (_i, [_vp] * 4 + [ctypes.c_int64, _i, ctypes.c_float] + [_vp] * 5),
     "msda_layernorm_backward_f32": (_i, [_vp] * 5 + [ctypes.c_int64, _i] + [_vp] * 4),
     "msda_linear_tf32": (_i, [_vp] * 3 + [ctypes.c_int64, _i, _i, _vp, _vp]),
+    "msda_linear_tf32_ex": (_i, [_vp] * 4 + [ctypes.c_int64, _i, _i, _i, _vp, _vp]),
+    "msda_linear_tf32_ws_ok": (_i, [_i, _i]),
     "msda_condinst_forward_f32": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _vp]),
     "msda_condinst_backward_f32": (_i, [_vp] * 5 + [_i] * 6 + [_vp] * 4),
     "msda_aligned_bilinear_forward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, _i, _vp, _vp]),

@@ -15,9 +15,13 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/msda_b200.h"
+
+extern std::atomic<uint64_t> g_msda_gemm_launches;
+std::atomic<uint64_t> g_msda_gemm_launches{0};
 
 namespace gemm {
 
@@ -237,6 +241,150 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols) : "memory");
 }
 
+// =====================================================================================================================
+// W-STATIONARY variant for the module's own shapes (K <= 256, N <= 256: value_proj / output_proj, 256 -> 256).
+//
+// The streaming kernel above re-reads W (256 KB) from L2 for every 128-row tile -- as many bytes as the A tile itself --
+// and its 48 KB stages leave room for 4 of them.  Here the roles of the pair's operands are swapped:
+//   * CTA r of the pair owns the output COLUMNS [r N/2, (r+1) N/2) and keeps its half of W (N/2 x K fp32 <= 128 KB)
+//     resident in shared memory for the whole kernel (loaded once);
+//   * both CTAs need the same A tile: each loads 64 of its 128 rows per k-block and TMA-multicasts them into both CTAs'
+//     stage, so A crosses L2 -> SM once per pair;  stages are 16 KB -> 5 in flight next to the resident W;
+//   * MMA stays cta_group::1 (M = 128, N = N/2), accumulators double-buffered in tensor memory;
+//   * epilogue straight from registers: tcgen05.ld gives every thread 32 consecutive columns of its row = one 128-byte
+//     segment, written with 16-byte stores after the fused tail  (+ bias) -> (row mask -> 0) -> (ReLU).
+// The row mask is ops/modules/ms_deform_attn.py:96-97 (`value.masked_fill(input_padding_mask[..., None], 0)`) folded into
+// value_proj's epilogue; ReLU is the FFN's first activation.
+struct ParamsWS {
+    long long M;
+    int N, K, stages, tmem_cols, relu;
+    const float *bias;
+    const unsigned char *row_mask;      // [M] bytes, non-zero = zero the whole output row; may be null
+    float *C;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ParamsWS p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NH = p.N / 2, KB = p.K / BLOCK_K;
+    const unsigned a_bytes = BLOCK_M * BLOCK_K * 4;                     // one A stage: 128 rows x 128 B
+    const unsigned wk_bytes = (unsigned)NH * BLOCK_K * 4;               // one k-block of this CTA's half of W
+    unsigned char *w_res = smem;                                        // KB x [NH x 128 B], resident
+    unsigned char *stages = smem + (size_t)KB * wk_bytes;
+    const long long ntiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const unsigned rank = cluster_ctarank();
+    const long long tile0 = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((unsigned)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: W once, then the A stream =====
+        if (lane == 0) {
+            mbar_expect_tx(&w_bar, (unsigned)KB * wk_bytes);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(w_res + (size_t)kb * wk_bytes, &map_w, kb * BLOCK_K, (int)rank * NH, &w_bar);
+            unsigned it = 0;
+            for (long long t = tile0; t < ntiles; t += tile_stride) {
+                const int row0 = (int)(t * BLOCK_M) + (int)rank * (BLOCK_M / 2);       // this CTA's 64 rows of the shared tile
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);                    // both CTAs' MMAs have drained this stage
+                    mbar_expect_tx(&full_bar[s], a_bytes);               // own half + the peer's half
+                    tma_load_2d_mc(stages + (size_t)s * a_bytes + (size_t)rank * (a_bytes / 2), &map_a, kb * BLOCK_K, row0,
+                                   &full_bar[s], (uint16_t)3);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        mbar_wait(&w_bar, 0);
+        unsigned it = 0, tt = 0;
+        const uint32_t idesc = umma_idesc_tf32(BLOCK_M, NH);
+        for (long long t = tile0; t < ntiles; t += tile_stride, ++tt) {
+            const unsigned buf = tt & 1, use = tt >> 1;
+            mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_base + buf * (uint32_t)NH;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const unsigned char *sa = stages + (size_t)s * a_bytes;
+                    const unsigned char *sw = w_res + (size_t)kb * wk_bytes;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_tf32(acc, umma_desc(sa, k * UMMA_K * 4), umma_desc(sw, k * UMMA_K * 4), idesc, (kb | k) != 0);
+                    umma_commit_mc(&empty_bar[s], (uint16_t)3);          // stage free in BOTH CTAs once both have committed
+                    if (kb == KB - 1) umma_commit(&tmem_full_bar[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias, mask, ReLU) -> 128-byte row segments =====
+        const int lane_base = (warp & 3) * 32;
+        unsigned tt = 0;
+        for (long long t = tile0; t < ntiles; t += tile_stride, ++tt) {
+            const unsigned buf = tt & 1, use = tt >> 1;
+            mbar_wait(&tmem_full_bar[buf], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = t * BLOCK_M + lane_base + lane;
+            const bool live = row < p.M;
+            const bool dead = live && p.row_mask != nullptr && p.row_mask[row] != 0;
+            float *crow = p.C + (live ? row : 0) * (long long)p.N + (long long)rank * NH;
+            for (int c0 = 0; c0 < NH; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)NH + (uint32_t)c0, v);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (p.bias != nullptr) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + (size_t)rank * NH + c0 + i));
+                            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                        }
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (dead) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(crow + c0 + i) = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[buf])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols) : "memory");
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -269,8 +417,65 @@ bool make_map(CUtensorMap *map, const float *base, long long rows, int K, int bo
 
 }  // namespace gemm
 
-extern std::atomic<uint64_t> g_msda_gemm_launches;
-std::atomic<uint64_t> g_msda_gemm_launches{0};
+namespace gemm {
+
+// W-stationary eligibility: the pair's halves of W must fit next to >= 3 A stages.
+bool ws_ok(int N, int K) {
+    if (N % 64 || N < 64 || N > 256 || K % BLOCK_K) return false;
+    const size_t w_half = (size_t)(N / 2) * K * 4;
+    return w_half + 3u * (BLOCK_M * BLOCK_K * 4) + 2048 <= 232448 - 1024;
+}
+
+int sms_for_device(const void *kernel, int smem_bytes, std::atomic<int> (&cache)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int sms = cache[dev].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev].store(sms, std::memory_order_relaxed);
+    }
+    return sms;
+}
+
+int launch_ws(const float *A, const float *W, const float *bias, const unsigned char *row_mask, long long M, int N, int K,
+              int relu, float *C, cudaStream_t stream) {
+    CUtensorMap map_a, map_w;
+    if (!make_map(&map_a, A, M, K, BLOCK_M / 2) || !make_map(&map_w, W, N, K, N / 2)) return MSDA_E_NODEVICE;
+    ParamsWS p;
+    p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
+    const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
+    constexpr size_t kDynMax = 232448 - 1024;
+    int stages = (int)((kDynMax - 1024 - w_half) / a_stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return MSDA_E_BADARG;
+    p.stages = stages;
+    p.tmem_cols = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;          // 2 accumulators of N/2 columns
+    const size_t smem = w_half + (size_t)stages * a_stage + 1024;
+    static std::atomic<int> cache[64];
+    const int sms = sms_for_device(reinterpret_cast<const void *>(linear_tf32_ws_kernel), (int)kDynMax, cache);
+    if (sms < 0) return MSDA_E_NODEVICE;
+    const long long tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const long long max_clusters = sms / 2;
+    const unsigned grid = 2u * (unsigned)(tiles < max_clusters ? tiles : max_clusters);
+    linear_tf32_ws_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, p);
+    g_msda_gemm_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace gemm
+
+extern "C" int msda_linear_tf32_ex(const float *A, const float *W, const float *bias, const uint8_t *row_mask, int64_t M, int N,
+                                   int K, int relu, float *C, void *stream) {
+    using namespace gemm;
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) return MSDA_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15u) return MSDA_E_BADARG;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return MSDA_E_BADARG;
+    if (!ws_ok(N, K)) return MSDA_E_BADARG;
+    return launch_ws(A, W, bias, row_mask, M, N, K, relu ? 1 : 0, C, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msda_linear_tf32_ws_ok(int N, int K) { return gemm::ws_ok(N, K) ? 1 : 0; }
 
 extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t M, int N, int K, float *C,
                                 void *stream) {
@@ -278,6 +483,11 @@ extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bia
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || K % BLOCK_K || N % 32 || N > kMaxN) return MSDA_E_BADARG;   // epilogue reads 32 TMEM columns at a time
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15u) return MSDA_E_BADARG;
     if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return MSDA_E_BADARG;
+    {
+        static int ws = -1;
+        if (ws < 0) { const char *e = getenv("MSDA_GEMM_WS"); ws = (e && e[0] == '0') ? 0 : 1; }
+        if (ws && ws_ok(N, K)) return launch_ws(A, W, bias, nullptr, M, N, K, 0, C, static_cast<cudaStream_t>(stream));
+    }
     if (N > 256 && (N % 64)) return MSDA_E_BADARG;      // MMA N tiles are multiples of 16, W halves whole swizzle atoms
     const int w_box_rows = N / 2;                       // each CTA of the pair loads (and multicasts) half of W
     CUtensorMap map_a, map_w;

@@ -76,48 +76,91 @@ def tcgen05_linear(x2: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor
     return out
 
 
+def resolve_gemm(gemm: str) -> str:
+    """"auto": the hand-written tcgen05 TF32 kernels when the caller has allowed TF32 products
+    (``torch.backends.cuda.matmul.allow_tf32`` -- the default of the PyTorch 1.10 stack the reference was trained with), cuBLAS
+    fp32 otherwise, so that strict-fp32 runs keep their 1e-4 parity with the reference."""
+    if gemm == "auto":
+        return "tcgen05" if torch.backends.cuda.matmul.allow_tf32 else "cublas"
+    return gemm
+
+
+def tcgen05_ws_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
+    """W-stationary kernel with the fused tail (msda_linear_tf32_ex): K <= 256, N <= 256, N % 64 == 0."""
+    n, k = weight.shape
+    return tcgen05_linear_ok(x2, weight) and bool(_cabi.load().msda_linear_tf32_ws_ok(n, k))
+
+
+def tcgen05_linear_ex(x2, weight, bias, row_mask=None, relu=False):
+    """x2 @ weight.T + bias, rows with ``row_mask`` set written as zeros, optional ReLU -- one kernel (msda_linear_tf32_ex)."""
+    x2, weight = x2.contiguous(), weight.contiguous()
+    m, k = x2.shape
+    n = weight.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x2.device)
+    mask8 = None
+    if row_mask is not None:
+        mask8 = row_mask.reshape(-1).to(torch.uint8).contiguous()          # bool -> bytes (a view-compatible copy, M bytes)
+    with torch.cuda.device(x2.device):
+        _cabi.check(_cabi.load().msda_linear_tf32_ex(x2.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                     mask8.data_ptr() if mask8 is not None else None, m, n, k, int(relu),
+                                                     out.data_ptr(), _stream()), "msda_linear_tf32_ex")
+    return out
+
+
 def _gemm_bias(x2, weight, bias, gemm):
-    if gemm == "tcgen05" and tcgen05_linear_ok(x2, weight):
+    if resolve_gemm(gemm) == "tcgen05" and tcgen05_linear_ok(x2, weight):
         return tcgen05_linear(x2, weight, bias)
     return torch.addmm(bias, x2, weight.t())
 
 
 class _LinearColsum(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, gemm):
+    def forward(ctx, x, weight, bias, relu, gemm, row_mask):
         x2 = x.reshape(-1, x.shape[-1])
-        if relu:                                             # bias + ReLU in the cuBLASLt epilogue
+        mask = row_mask.reshape(-1) if row_mask is not None else None
+        if resolve_gemm(gemm) == "tcgen05" and tcgen05_ws_ok(x2, weight):
+            y = tcgen05_linear_ex(x2, weight, bias, mask, relu)          # bias, padding-mask zeroing and ReLU in the epilogue
+        elif relu:                                           # bias + ReLU in the cuBLASLt epilogue
             y = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)
-            ctx.save_for_backward(x2, weight, y)
+            if mask is not None:
+                y = y.masked_fill(mask[:, None], 0.0)
         else:
             y = _gemm_bias(x2, weight, bias, gemm)
-            ctx.save_for_backward(x2, weight)
+            if mask is not None:
+                y = y.masked_fill(mask[:, None], 0.0)
+        ctx.save_for_backward(x2, weight, y if relu else None, mask)
         ctx.xshape, ctx.relu = x.shape, relu
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x2, weight = ctx.saved_tensors[:2]
+        x2, weight, y, mask = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
         if ctx.relu:
-            g2 = torch.ops.aten.threshold_backward(g2, ctx.saved_tensors[2], 0.0)
+            g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)          # masked rows have y == 0: already zeroed
+        elif mask is not None:
+            g2 = g2.masked_fill(mask[:, None], 0.0)
         else:
             g2 = g2.contiguous()
         gx = torch.mm(g2, weight).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         gw = weight_grad(g2, x2) if ctx.needs_input_grad[1] else None
         gb = colsum(g2) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False, gemm: str = "cublas"):
-    """``linear(x)`` (optionally followed by ReLU) with the bias gradient computed by msda_colsum_f32 and the weight
-    gradient as a split-K batched GEMM.  ``gemm="tcgen05"`` runs the forward product on msda_linear_tf32."""
+def linear_colsum(x, linear: torch.nn.Linear, relu: bool = False, gemm: str = "cublas", row_mask=None):
+    """``linear(x)`` (optionally followed by ReLU, optionally with the rows of ``row_mask`` zeroed -- the
+    ``masked_fill(input_padding_mask)`` after value_proj) with the bias gradient computed by msda_colsum_f32 and the
+    weight gradient as a split-K batched GEMM.  ``gemm="tcgen05"`` / ``"auto"`` (under allow_tf32) runs the forward product
+    on the hand-written tensor-core kernels, with bias / mask / ReLU fused into their epilogue for K, N <= 256."""
     if (not x.is_cuda) or x.dtype != torch.float32 or linear.bias is None or linear.out_features % 4 or \
             torch.is_autocast_enabled():
         y = linear(x)
-        return torch.relu(y) if relu else y
-    return _LinearColsum.apply(x, linear.weight, linear.bias, relu, gemm)
+        if relu:
+            y = torch.relu(y)
+        return y if row_mask is None else y.masked_fill(row_mask[..., None], 0.0)
+    return _LinearColsum.apply(x, linear.weight, linear.bias, relu, gemm, row_mask)
 
 
 class _BatchedLinear(Function):

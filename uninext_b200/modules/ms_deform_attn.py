@@ -53,7 +53,7 @@ def _power_of_two(n: int) -> bool:
 
 
 class MSDeformAttn(nn.Module):
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None, fused=True, gemm="cublas"):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, op_dtype=None, fused=True, gemm="auto"):
         super().__init__()
         if d_model % n_heads:
             raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
@@ -64,8 +64,11 @@ class MSDeformAttn(nn.Module):
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.op_dtype = op_dtype
         self.fused = fused           # one-pass prologue / bias-gradient kernels around the GEMMs (same maths)
-        # "cublas" (default: measured faster) or "tcgen05": forward products of value_proj / output_proj / the sampling
-        # projection on the hand-written TF32 tensor-core kernel msda_linear_tf32 (TF32 rounding, like allow_tf32)
+        # forward products of value_proj / output_proj / the sampling projection:
+        #   "auto"    (default) hand-written tcgen05 TF32 kernels when torch.backends.cuda.matmul.allow_tf32 is set (TF32
+        #             rounding is then what the caller asked for), cuBLAS fp32 otherwise (1e-4 parity with the reference);
+        #   "tcgen05" / "cublas" force one or the other.
+        # value_proj's bias and padding-mask zeroing ride in the tcgen05 kernel's epilogue (no masked_fill pass).
         self.gemm = gemm
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
@@ -112,9 +115,12 @@ class MSDeformAttn(nn.Module):
         if projected_value is not None:        # value_proj (+ padding mask) already applied, e.g. batched over decoder layers
             value = projected_value
         else:
-            value = linear_colsum(input_flatten, self.value_proj, gemm=self.gemm) if fused else self.value_proj(input_flatten)
-            if input_padding_mask is not None:
-                value = value.masked_fill(input_padding_mask[..., None], 0.0)
+            if fused:      # bias + padding-mask zeroing in the GEMM epilogue (ms_deform_attn.py:95-97 as one kernel)
+                value = linear_colsum(input_flatten, self.value_proj, gemm=self.gemm, row_mask=input_padding_mask)
+            else:
+                value = self.value_proj(input_flatten)
+                if input_padding_mask is not None:
+                    value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(n, s, m, self.d_model // m)
         if fused:
             loc, weights = sampling_prologue(query, self.sampling_offsets, self.attention_weights, reference_points,
