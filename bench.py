@@ -380,7 +380,9 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
     from uninext_b200.workloads import level_tensors
     torch.manual_seed(1234)                                   # identical weights on every rank
     model = DeformableStack(num_layers=6, num_queries=cfg.dec_queries).to(device)
-    bucket = FlatGradBucket(model.parameters())
+    # gradient exchange overlapped with backward: 8 MB slices of the flat buffer are all-reduced from grad hooks as soon as
+    # backward has filled them (DDP's behaviour, detectron2/engine/defaults.py:60-79); single GPU: nothing to exchange
+    bucket = FlatGradBucket(model.parameters(), overlap=world > 1)
     shapes = cfg.shapes
     ss, lsi = level_tensors(shapes, device)
     g = torch.Generator(device=device).manual_seed(77 + rank)
@@ -392,7 +394,7 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
             out = model(src, pos, shapes, ss, lsi)
         out.float().square().mean().backward()
-        bucket.all_reduce_mean()
+        bucket.finish()
 
     def measure(amp):
         for _ in range(3):
@@ -432,6 +434,7 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
     # Whole step captured in a CUDA graph (launch-bound otherwise: ~1000 kernels, 15 ms of device work in a 20 ms step);
     # the gradient all-reduce stays outside the graph and runs after each replay.
     torch.backends.cuda.matmul.allow_tf32 = True
+    overlap_was, bucket.overlap = bucket.overlap, False        # no collectives inside the captured graph
     try:
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream())
@@ -454,7 +457,10 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
         res["tf32_cuda_graph"] = _measure_with(graphed_step, steps, barrier, lib, world, device, cfg)
     except Exception as exc:               # capture is an optimisation; report why it was not available
         res["tf32_cuda_graph"] = {"unavailable": repr(exc)[:200]}
+    bucket.overlap = overlap_was
     torch.backends.cuda.matmul.allow_tf32 = old
+    res["grad_exchange"] = (f"overlapped: {bucket.n_slices} slices all-reduced from grad hooks during backward (eager legs); "
+                            "one flat all-reduce after the replay (cuda-graph leg)") if world > 1 else "single GPU: none"
     return res
 
 
@@ -480,8 +486,31 @@ def _measure_with(step_fn, steps, barrier, lib, world, device, cfg):
             "msda_launches_per_step_host": int((lib.msda_launch_count() - l0) / steps)}
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank's host threads to the NUMA node its GPU hangs off, so that the pinned e2e buffers it allocates next
+    are first-touched on that node: with 8 ranks, buffers on the far socket share one inter-socket link and the PCIe copies
+    of every rank slow down together (round 1: 33 % of linear at 8 GPUs).  Best effort; returns what was done."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError) as exc:
+        return {"numa_node": None, "note": repr(exc)[:120]}
+
+
 def run_e2e(MSDA, calls, op_args, world, smp_step, steps, device, barrier):
     """Same step, but inputs start in pinned host memory and results end there."""
+    numa = bind_to_gpu_numa_node(device)
     host_in, host_out, dev_in = [], [], []
     h2d = d2h = 0
     for c in calls:
@@ -549,7 +578,7 @@ def run_e2e(MSDA, calls, op_args, world, smp_step, steps, device, barrier):
     return {"value": round(world * smp_step / (ms * 1e-3) / 1e9, 4), "unit": UNIT, "ms_per_step": round(ms, 3),
             "steps": steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "api": "MultiScaleDeformableAttention.ms_deform_attn_forward/backward on pinned-host inputs; "
-                   "H2D / kernels / D2H on three streams"}
+                   "H2D / kernels / D2H on three streams", "host_numa": numa}
 
 
 # ------------------------------------------------------------------------------------------------------------------

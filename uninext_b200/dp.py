@@ -70,8 +70,8 @@ class FlatGradBucket:
         self._works = []
         self._next = len(self._slices) - 1               # slices are launched last-to-first (backward order)
         self._hooks = []
-        if self.overlap:
-            for i, p in enumerate(self.params):
+        if self.overlap:                    # hooks stay registered; `self.overlap = False` silences them (e.g. while a
+            for i, p in enumerate(self.params):     # CUDA graph of the step is captured: collectives stay outside the graph)
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
         self._arm()
 
@@ -115,6 +115,8 @@ class FlatGradBucket:
 
     def _make_hook(self, i):
         def hook(p):
+            if not self.overlap:
+                return
             v = self._views[i]
             if p.grad is not v and (p.grad is None or p.grad.data_ptr() != v.data_ptr()):
                 v.copy_(p.grad)                      # the aliasing was broken since the last step: repair in place
