@@ -31,5 +31,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(((e.device_time_total / 2, e.count // 2, e.key) for e in prof.key_averages() if e.device_time_total > 0), reverse=True)
 dev_ms = sum(r[0] for r in rows) / 1e3
 print(f"wall {wall*1e3:.2f} ms/step, device busy {dev_ms:.2f} ms/step, kernels/step {sum(r[1] for r in rows)}")
-for t_, c, k in rows[:14]:
+for t_, c, k in rows[:28]:
     print(f"{t_:9.1f} us  x{c:<4d} {k[:100]}")

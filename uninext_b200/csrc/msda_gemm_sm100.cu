@@ -258,13 +258,15 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 struct ParamsWS {
     long long M;
     int N, K, stages, tmem_cols, relu;
+    int multicast;                      // 1: the pair shares each A tile by TMA multicast; 0: every CTA loads its own copy
     const float *bias;
     const unsigned char *row_mask;      // [M] bytes, non-zero = zero the whole output row; may be null
     float *C;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ParamsWS p)
+linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_full,
+                      const __grid_constant__ CUtensorMap map_w, const ParamsWS p)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -284,7 +286,8 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_full) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.multicast ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
         mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -311,10 +314,13 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const int row0 = (int)(t * BLOCK_M) + (int)rank * (BLOCK_M / 2);       // this CTA's 64 rows of the shared tile
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);                    // both CTAs' MMAs have drained this stage
-                    mbar_expect_tx(&full_bar[s], a_bytes);               // own half + the peer's half
-                    tma_load_2d_mc(stages + (size_t)s * a_bytes + (size_t)rank * (a_bytes / 2), &map_a, kb * BLOCK_K, row0,
-                                   &full_bar[s], (uint16_t)3);
+                    mbar_wait(&empty_bar[s], ph ^ 1);                    // the MMAs (of both CTAs when sharing) have drained it
+                    mbar_expect_tx(&full_bar[s], a_bytes);               // whole tile: own half + the peer's half, or own copy
+                    if (p.multicast)
+                        tma_load_2d_mc(stages + (size_t)s * a_bytes + (size_t)rank * (a_bytes / 2), &map_a, kb * BLOCK_K, row0,
+                                       &full_bar[s], (uint16_t)3);
+                    else
+                        tma_load_2d(stages + (size_t)s * a_bytes, &map_a_full, kb * BLOCK_K, (int)(t * BLOCK_M), &full_bar[s]);
                 }
             }
         }
@@ -338,7 +344,8 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                         umma_tf32(acc, umma_desc(sa, k * UMMA_K * 4), umma_desc(sw, k * UMMA_K * 4), idesc, (kb | k) != 0);
-                    umma_commit_mc(&empty_bar[s], (uint16_t)3);          // stage free in BOTH CTAs once both have committed
+                    if (p.multicast) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // free in BOTH CTAs once both have committed
+                    else umma_commit(&empty_bar[s]);
                     if (kb == KB - 1) umma_commit(&tmem_full_bar[buf]);
                 }
                 __syncwarp();
@@ -454,9 +461,13 @@ int sms_for_device(const void *kernel, int smem_bytes, std::atomic<int> (&cache)
 
 int launch_ws(const float *A, const float *W, const float *bias, const unsigned char *row_mask, long long M, int N, int K,
               int relu, float *C, cudaStream_t stream) {
-    CUtensorMap map_a, map_w;
-    if (!make_map(&map_a, A, M, K, BLOCK_M / 2) || !make_map(&map_w, W, N, K, N / 2)) return MSDA_E_NODEVICE;
+    CUtensorMap map_a, map_a_full, map_w;
+    if (!make_map(&map_a, A, M, K, BLOCK_M / 2) || !make_map(&map_a_full, A, M, K, BLOCK_M) || !make_map(&map_w, W, N, K, N / 2))
+        return MSDA_E_NODEVICE;
+    static int mc = -1;
+    if (mc < 0) { const char *e = getenv("MSDA_GEMM_WS_MC"); mc = (e && e[0] == '0') ? 0 : 1; }
     ParamsWS p;
+    p.multicast = mc;
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
     const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
     constexpr size_t kDynMax = 232448 - 1024;
@@ -473,7 +484,7 @@ int launch_ws(const float *A, const float *W, const float *bias, const unsigned 
     const long long tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const long long max_clusters = sms / 2;
     const unsigned grid = 2u * (unsigned)(tiles < max_clusters ? tiles : max_clusters);
-    linear_tf32_ws_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, p);
+    linear_tf32_ws_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_a_full, map_w, p);
     g_msda_gemm_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }

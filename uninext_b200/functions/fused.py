@@ -76,12 +76,18 @@ def tcgen05_linear(x2: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor
     return out
 
 
+# "auto" picks the hand-written kernels only where they are the faster choice.  Measured on B200 (profiles/r02*_gemm*.txt):
+# cuBLAS TF32 is still ahead on these shapes, so auto resolves to cuBLAS unless MSDA_GEMM_AUTO=tcgen05 is set.
+import os as _os
+_AUTO_TCGEN05 = _os.environ.get("MSDA_GEMM_AUTO", "cublas") == "tcgen05"
+
+
 def resolve_gemm(gemm: str) -> str:
     """"auto": the hand-written tcgen05 TF32 kernels when the caller has allowed TF32 products
     (``torch.backends.cuda.matmul.allow_tf32`` -- the default of the PyTorch 1.10 stack the reference was trained with), cuBLAS
     fp32 otherwise, so that strict-fp32 runs keep their 1e-4 parity with the reference."""
     if gemm == "auto":
-        return "tcgen05" if torch.backends.cuda.matmul.allow_tf32 else "cublas"
+        return "tcgen05" if (torch.backends.cuda.matmul.allow_tf32 and _AUTO_TCGEN05) else "cublas"
     return gemm
 
 
