@@ -254,10 +254,13 @@ def run_b200(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": b_bwd,
                 "traffic": ncu_traffic(f"{args.config}_enc_{'f32' if args.dtype == 'fp32' else 'bf16'}", "bwd"),
                 "traffic_note": "kernel only (the 45.7 MB grad_value memset is a separate launch); profiles/ncu_traffic.json",
-                "binding_ceiling": "L2 vector atomics: red.global.add.v4.f32 on random 128-B rows sustains 5.7-6.4 TB/s "
-                                   "payload on this GPU (profiles/r01g_ubench_lsu_gather_ceiling.txt); the backward must "
-                                   "push 2.5 GB of them per call -> 390-440 us; forward is bound by the LSU gather rate "
-                                   "(68 B/clk/SM for L2-resident rows -> 147 us)",
+                "binding_ceiling": "backward: each SM's path into the crossbar carries ~25 B/clk of red.global payload (21.8 with all "
+                                   "148 SMs active; scales with the SM count, independent of the hot-set size -> it is not the L2 "
+                                   "atomic units; profiles/r02b_ubench_smem_rmw_and_egress.txt); the op must add 4 x 128 B per tap "
+                                   "(2.5 GB per call) -> 393 us + gathers.  Combining rows inside the SM removes egress one for one "
+                                   "but costs 4 shared-memory wavefronts per row on the LSU data pipe the gathers already keep > 50 % "
+                                   "busy (slab kernels: -43 % red sectors, +36 % time; profiles/r02c_slab_kernels_ncu.md).  forward: "
+                                   "LSU data pipe 66-72 % busy moving 2.93 GB of rows per call (>= 155 k wavefronts per SM)",
                 "enc_fwd": {"achieved": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9, 1),
                             "frac": round(b_fwd / (kern["enc_fwd_ms"] * 1e-3) / 1e9 / peak, 4),
                             "algorithmic_bytes_per_launch": b_fwd}}

@@ -41,7 +41,7 @@ if not ok:
     sys.exit(1)
 torch.backends.cuda.matmul.allow_tf32 = True
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for (m, n, k) in [(44646, 256, 256), (65280, 256, 256), (25500, 256, 256)]:
+for (m, n, k) in [(44646, 256, 256), (65280, 256, 256), (25500, 256, 256), (44646, 128, 256), (44646, 256, 128)]:
     a = torch.randn(m, k, device="cuda"); w = torch.randn(n, k, device="cuda") * 0.1; b = torch.randn(n, device="cuda")
     c = torch.empty(m, n, device="cuda")
     def stream_kernel():

@@ -57,6 +57,10 @@ __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map
                  "[%0], [%1, {%2, %3}], [%4], %5;"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier): hides the DRAM part of a later tile load's latency
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -310,8 +314,16 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(w_res + (size_t)kb * wk_bytes, &map_w, kb * BLOCK_K, (int)rank * NH, &w_bar);
             unsigned it = 0;
+            // The ring holds only 4-5 A stages next to the resident W (64-80 KB in flight per SM), too little to cover the
+            // DRAM latency of a tile load: each CTA therefore prefetches ITS half of the NEXT tile into L2 (no smem, no
+            // barrier) while the current tile streams, so that the ring's loads are L2 hits.
+            for (int kb = 0; kb < KB && tile0 < ntiles; ++kb)
+                tma_prefetch_2d(&map_a, kb * BLOCK_K, (int)(tile0 * BLOCK_M) + (int)rank * (BLOCK_M / 2));
             for (long long t = tile0; t < ntiles; t += tile_stride) {
                 const int row0 = (int)(t * BLOCK_M) + (int)rank * (BLOCK_M / 2);       // this CTA's 64 rows of the shared tile
+                if (t + tile_stride < ntiles)
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_prefetch_2d(&map_a, kb * BLOCK_K, (int)((t + tile_stride) * BLOCK_M) + (int)rank * (BLOCK_M / 2));
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);                    // the MMAs (of both CTAs when sharing) have drained it
