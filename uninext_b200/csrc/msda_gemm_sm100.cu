@@ -263,6 +263,7 @@ struct ParamsWS {
     long long M;
     int N, K, stages, tmem_cols, relu;
     int multicast;                      // 1: the pair shares each A tile by TMA multicast; 0: every CTA loads its own copy
+    int direct_epilogue;                // 1: registers -> 32-byte global stores (no shared memory); 0: smem transpose
     const float *bias;
     const unsigned char *row_mask;      // [M] bytes, non-zero = zero the whole output row; may be null
     float *C;
@@ -386,6 +387,34 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (r < p.M && p.row_mask[r] != 0) dead_bits |= 1u << i;
                 }
             }
+            if (p.direct_epilogue) {
+                // The tf32 MMA reads its operands from shared memory at ~119 B/clk (8 KB per 69-cycle instruction) -- the
+                // whole shared-memory port.  A transpose through shared memory therefore cannot overlap the next tile's
+                // MMAs (measured: MMA phase + epilogue ADD UP, 4.1 us per tile).  Here every thread writes its own row
+                // straight from registers, one full 32-byte sector per store.
+                const long long r = row_base + lane;
+                const bool live = r < p.M;
+                const bool dead = live && p.row_mask != nullptr && p.row_mask[r] != 0;
+                float *crow = p.C + (live ? r : 0) * (long long)p.N + (long long)rank * NH;
+                for (int c0 = 0; c0 < NH; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)NH + (uint32_t)c0, v);
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                o[e] = v[i + e] + (p.bias != nullptr ? __ldg(p.bias + (size_t)rank * NH + c0 + i + e) : 0.f);
+                                if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                                if (dead) o[e] = 0.f;
+                            }
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c0 + i), "f"(o[0]),
+                                         "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+                        }
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < NH; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)NH + (uint32_t)c0, v);
@@ -478,8 +507,11 @@ int launch_ws(const float *A, const float *W, const float *bias, const unsigned 
         return MSDA_E_NODEVICE;
     static int mc = -1;
     if (mc < 0) { const char *e = getenv("MSDA_GEMM_WS_MC"); mc = (e && e[0] == '0') ? 0 : 1; }
+    static int direct = -1;
+    if (direct < 0) { const char *e = getenv("MSDA_GEMM_WS_EPI"); direct = (e && e[0] == 't') ? 0 : 1; }      // "transpose" -> 0
     ParamsWS p;
     p.multicast = mc;
+    p.direct_epilogue = (direct && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0) && (N % 16 == 0)) ? 1 : 0;
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
     const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
     constexpr size_t kDynMax = 232448 - 1024;
