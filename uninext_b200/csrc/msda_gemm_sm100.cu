@@ -387,7 +387,14 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (r < p.M && p.row_mask[r] != 0) dead_bits |= 1u << i;
                 }
             }
-            if (p.direct_epilogue) {
+            if (p.direct_epilogue >= 2) {            // timing experiments: 2 = nothing, 3 = TMEM loads only
+                if (p.direct_epilogue == 3)
+                    for (int c0 = 0; c0 < NH; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)NH + (uint32_t)c0, v);
+                        if (v[0] == 123.456f && row_base < 0) p.C[0] = v[1];
+                    }
+            } else if (p.direct_epilogue) {
                 // The tf32 MMA reads its operands from shared memory at ~119 B/clk (8 KB per 69-cycle instruction) -- the
                 // whole shared-memory port.  A transpose through shared memory therefore cannot overlap the next tile's
                 // MMAs (measured: MMA phase + epilogue ADD UP, 4.1 us per tile).  Here every thread writes its own row
@@ -507,11 +514,16 @@ int launch_ws(const float *A, const float *W, const float *bias, const unsigned 
         return MSDA_E_NODEVICE;
     static int mc = -1;
     if (mc < 0) { const char *e = getenv("MSDA_GEMM_WS_MC"); mc = (e && e[0] == '0') ? 0 : 1; }
+    // epilogue: 0 = shared-memory transpose (default, measured faster), 1 = "direct" register stores;
+    // 2 = "none", 3 = "ldonly": TIMING EXPERIMENTS ONLY (no / partial output), never used by the library's callers
     static int direct = -1;
-    if (direct < 0) { const char *e = getenv("MSDA_GEMM_WS_EPI"); direct = (e && e[0] == 't') ? 0 : 1; }      // "transpose" -> 0
+    if (direct < 0) {
+        const char *e = getenv("MSDA_GEMM_WS_EPI");
+        direct = (e && e[0] == 'd') ? 1 : (e && e[0] == 'n') ? 2 : (e && e[0] == 'l') ? 3 : 0;
+    }
     ParamsWS p;
     p.multicast = mc;
-    p.direct_epilogue = (direct && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0) && (N % 16 == 0)) ? 1 : 0;
+    p.direct_epilogue = direct >= 2 ? direct : (direct == 1 && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0) && (N % 16 == 0)) ? 1 : 0;
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
     const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
     constexpr size_t kDynMax = 232448 - 1024;
