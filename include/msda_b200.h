@@ -63,8 +63,9 @@ uint64_t msda_launch_count(void);
  * MSDA_ prefix, e.g. MSDA_SLAB=0).  They never change results, only which kernel computes them; the tests use
  * them to run every kernel family on small shapes, the tools to sweep them.  Returns the previous value, or
  * MSDA_E_BADARG for an unknown knob.  value == MSDA_KNOB_QUERY reads without writing.
- *   MSDA_KNOB_SLAB          1 = slab-ordered kernels (msda_slab.cuh) whenever D == 32 and L*P <= 16; -1 (auto) and 0 = tiled
- *                           kernels (the measured-faster default)
+ *   MSDA_KNOB_SLAB          1 = slab-ordered kernels (msda_slab.cuh) whenever D == 32 and L*P <= 16; 2 = tiled forward +
+ *                           backward with tensor-memory accumulators for the coarse levels (msda_tmem.cuh); -1 (auto) and
+ *                           0 = tiled kernels
  *   MSDA_KNOB_BWD_WIN_ROWS  shared-memory window of the slab backward in rows of 128 B (-1 = all that fits)
  *   MSDA_KNOB_BWD_LIST_CAP  entries per row-class list of the slab backward (even, >= 8)
  *   MSDA_KNOB_FWD_SLAB_CTAS resident CTAs per SM of the slab forward (1 or 2)

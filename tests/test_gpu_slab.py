@@ -180,3 +180,47 @@ def test_bf16_backward_mixed_accumulation_vs_oracle(knobs, fine_rows):
     out, gv, gl, ga = _check(inp, 1e-2)
     assert gv.dtype == torch.bfloat16
     assert knobs.msda_launch_count() - before == 4          # forward, zero coarse scratch rows, backward, round coarse rows
+
+
+# ---- tensor-memory backward (msda_tmem.cuh, MSDA_KNOB_SLAB = 2): coarse levels of grad_value accumulated in TMEM columns ----
+@pytest.mark.parametrize("kind", ["enc", "dec"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("list_cap", [48, 8])                  # 8: producer lists overflow -> red.global fallback
+def test_tmem_backward_vs_oracle_cfg1(knobs, kind, dtype, tol, list_cap):
+    knobs.msda_set_knob(_cabi.KNOB_SLAB, 2)
+    knobs.msda_set_knob(_cabi.KNOB_BWD_LIST_CAP, list_cap)
+    _check(make_inputs(CONFIGS["cfg1"], kind, DEV, dtype=dtype, seed=41, wild_fraction=0.1), tol)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(shapes=[(7, 9)], N=1, M=1, Lq=1, P=1),
+    dict(shapes=[(5, 6), (3, 3)], N=3, M=5, Lq=13, P=3),
+    dict(shapes=[(9, 11), (4, 5), (2, 3), (1, 1)], N=2, M=3, Lq=150, P=4),          # 4 tiles of 48 pairs per slab, last partial
+    dict(shapes=[(4, 4)] * 8, N=1, M=2, Lq=70, P=2),
+    dict(shapes=[(40, 60), (3, 3)], N=1, M=2, Lq=100, P=4),                         # 2400 rows > 2048: only the small level fits
+])
+def test_tmem_backward_ragged_vs_oracle(knobs, shape):
+    knobs.msda_set_knob(_cabi.KNOB_SLAB, 2)
+    g = torch.Generator().manual_seed(43)
+    ss = torch.as_tensor(shape["shapes"], dtype=torch.long)
+    L = ss.shape[0]
+    lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    S = int(ss.prod(1).sum())
+    N, M, Lq, P = (shape[k] for k in ("N", "M", "Lq", "P"))
+    inp = dict(
+        value=torch.randn(N, S, M, 32, generator=g).to(DEV), spatial_shapes=ss.to(DEV), level_start_index=lsi.to(DEV),
+        sampling_locations=(torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3).to(DEV),
+        attention_weights=torch.rand(N, Lq, M, L, P, generator=g).to(DEV),
+        grad_output=torch.randn(N, Lq, M * 32, generator=g).to(DEV))
+    _check(inp, 1e-4)
+
+
+def test_tmem_and_tiled_backward_agree_at_cfg2(knobs):
+    inp = make_inputs(CONFIGS["cfg2"], "enc", DEV, seed=45, wild_fraction=0.02)
+    knobs.msda_set_knob(_cabi.KNOB_SLAB, 0)
+    ref = _run(inp)
+    knobs.msda_set_knob(_cabi.KNOB_SLAB, 2)
+    got = _run(inp)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale, i

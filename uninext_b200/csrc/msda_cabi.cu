@@ -10,6 +10,7 @@
 #include "msda_generic.cuh"
 #include "msda_module.cuh"
 #include "msda_slab.cuh"
+#include "msda_tmem.cuh"
 #include "msda_tiled.cuh"
 
 namespace {
@@ -279,6 +280,32 @@ cudaError_t launch_bwd_mixed(const __nv_bfloat16 *go, const __nv_bfloat16 *value
     return cudaGetLastError();
 }
 
+// Backward with tensor-memory accumulators for the coarse levels (msda_tmem.cuh): MSDA_KNOB_SLAB = 2.
+template <typename T>
+cudaError_t launch_bwd_tmem(const T *grad_out, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+                            const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
+    static std::atomic<int> ready[kMaxDevices], cap_c[kMaxDevices], epoch_c[kMaxDevices];
+    const int dev = current_device();
+    const int epoch = knobs().epoch.load(std::memory_order_acquire);
+    auto kern = msda::msda_bwd_tmem<T, 16>;
+    int cap = cap_c[dev].load(std::memory_order_relaxed);
+    if (!ready[dev].load(std::memory_order_relaxed) || epoch_c[dev].load(std::memory_order_relaxed) != epoch) {
+        cap = knob(MSDA_KNOB_BWD_LIST_CAP) & ~1;
+        if (cap < 8) cap = 8;
+        if (cap > 128) cap = 128;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msda::bwd_tmem_smem_bytes(cap));
+        if (e != cudaSuccess) return e;
+        cap_c[dev].store(cap, std::memory_order_relaxed);
+        epoch_c[dev].store(epoch, std::memory_order_relaxed);
+        ready[dev].store(1, std::memory_order_relaxed);
+    }
+    const int sms = num_sms();
+    kern<<<sms, msda::kTmThreads, msda::bwd_tmem_smem_bytes(cap), st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L,
+                                                                        d.Lq, d.P, sms, cap, gv, gl, ga);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 #define MSDA_ROUTE_LP(T, DD, CALL)                                   \
     (LP <= 16 ? CALL<T, DD, 16> : CALL<T, DD, 32>)
 
@@ -306,6 +333,8 @@ template <typename T>
 cudaError_t bwd_fast(const T *go, const T *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                      const float *attn, const Dims &d, float *gv, float *gl, float *ga, cudaStream_t st) {
     const int LP = d.L * d.P;
+    if (knob(MSDA_KNOB_SLAB) == 2 && d.D == 32 && LP <= 16 && d.L <= msda::kMaxLevels)
+        return launch_bwd_tmem<T>(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
     if (use_slab(d, (unsigned)((long long)d.N * d.Lq * d.M), value, gv))
         return launch_bwd_slab<T>(go, value, shapes, lsi, loc, attn, d, gv, gl, ga, st);
     if constexpr (sizeof(T) == 4) {

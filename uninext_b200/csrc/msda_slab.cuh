@@ -43,7 +43,7 @@ struct SlabMap {
 // smallest first while they fit `win_cap_rows` (cfg2: 13x21 + 25x42 = 1323 rows).  Derived on the device from the
 // device-resident level table, like every other map in this library (no host read of spatial_shapes).
 __device__ __forceinline__ void build_slab_map(SlabMap &sm, const int64_t *shapes, const int64_t *lsi, int L, int N, int M,
-                                               int Lq, int win_cap_rows) {
+                                               int Lq, int win_cap_rows, int tile_pairs = kSlabTile) {
     if (threadIdx.x == 0) {
         int rows[kMaxLevels];
         for (int l = 0; l < L; ++l) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void build_slab_map(SlabMap &sm, const int64_t *shape
             used += rows[best];
         }
         sm.wrows = used;
-        sm.tiles_per_slab = (unsigned)((Lq + kSlabTile - 1) / kSlabTile);
+        sm.tiles_per_slab = (unsigned)((Lq + tile_pairs - 1) / tile_pairs);
         sm.ntiles = (unsigned)N * (unsigned)M * sm.tiles_per_slab;
     }
     __syncthreads();
