@@ -19,7 +19,8 @@ for kind in ("enc", "dec"):
 # round 2: slab-ordered kernels (shared-memory window + lists: the racecheck target), lane-shape and mixed-bf16 knobs
 from uninext_b200 import _cabi
 lib = _cabi.load()
-for knob, val, dts in ((_cabi.KNOB_SLAB, 1, (torch.float32, torch.bfloat16)), (_cabi.KNOB_F32_VEC8_FWD, 1, (torch.float32,)),
+for knob, val, dts in ((_cabi.KNOB_SLAB, 1, (torch.float32, torch.bfloat16)), (_cabi.KNOB_SLAB, 2, (torch.float32, torch.bfloat16)),
+                       (_cabi.KNOB_F32_VEC8_FWD, 1, (torch.float32,)),
                        (_cabi.KNOB_F32_VEC8_BWD, 1, (torch.float32,)), (_cabi.KNOB_BF16_FINE_ROWS, 500, (torch.bfloat16,))):
     old = lib.msda_set_knob(knob, val)
     for dt in dts:
