@@ -1,6 +1,7 @@
 """GPU tests (-m gpu) of the kernel families selected by `msda_set_knob`: the slab-ordered kernels
 (uninext_b200/csrc/msda_slab.cuh: LDG.256 forward, backward with a shared-memory window for the coarse levels of
-grad_value) and the 32-byte lane shape of the fp32 tiled kernels.  The knobs force them onto small and ragged problems
+grad_value), the backward with tensor-memory accumulators (msda_tmem.cuh), the 32-byte lane shape of the fp32 tiled
+kernels and the mixed bf16 / fp32 accumulation of the bf16 backward.  The knobs force them onto small and ragged problems
 so that every branch -- window level sets, list overflow falling back to red.global, partial tiles, CTAs spanning
 several slabs -- is compared with the fp64 oracle and with the default tiled kernels.
 

@@ -304,7 +304,8 @@ def add_layer_norm(a, b, norm: torch.nn.LayerNorm):
     cols = a.shape[-1]
     auto = torch.is_autocast_enabled()               # under autocast the inputs are cast to fp32 by custom_fwd
     ok = a.is_cuda and (a.dtype == torch.float32 or auto) and cols in (128, 256, 384, 512) and norm.elementwise_affine \
-        and norm.bias is not None and (b is None or b.dtype == torch.float32 or auto)
+        and norm.bias is not None and (b is None or b.dtype == torch.float32 or auto) \
+        and all(t is None or t.data_ptr() % 16 == 0 for t in (a, b, norm.weight, norm.bias))      # float4 loads in the kernels
     if not ok:
         return norm(a if b is None else a + b)
     return _AddLayerNorm.apply(a, b, norm.weight, norm.bias, norm.eps)
