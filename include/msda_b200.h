@@ -139,6 +139,9 @@ int msda_prologue_backward_f32(const float *grad_loc, const float *grad_attn, co
                                const int64_t *spatial_shapes, int64_t R, int M, int L, int P, int refdim,
                                float *grad_proj, void *stream);
 int msda_colsum_f32(const float *x, int64_t rows, int cols, float *out, void *stream);
+/* ReLU backward fused with the bias gradient of the Linear before it (FFN linear1): g2 = g where y > 0 else 0;
+ * colsum[c] = sum_r g2[r, c] (zero-filled by the callee).  cols % 4 == 0. */
+int msda_relu_backward_colsum_f32(const float *g, const float *y, int64_t rows, int cols, float *g2, float *colsum, void *stream);
 int msda_add_layernorm_forward_f32(const float *a, const float *b, const float *gamma, const float *beta,
                                    int64_t rows, int cols, float eps, float *z, float *y, float *mean, float *rstd,
                                    void *stream);

@@ -23,7 +23,7 @@ def _build(device):
     return cfg, model, src, pos, ss, lsi
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from uninext_b200.dp import FlatGradBucket, shard_frames
@@ -33,25 +33,30 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         cfg, model, src, pos, ss, lsi = _build(dev)
-        bucket = FlatGradBucket(model.parameters())
+        # overlap: the flat buffer is all-reduced in 256 KB slices from grad hooks while backward is still running
+        bucket = FlatGradBucket(model.parameters(), overlap=overlap, slice_bytes=256 << 10)
         idx = list(shard_frames(src.shape[0], world, rank))
-        out = model(src[idx], pos[idx], cfg.shapes, ss, lsi)
-        out.square().mean().backward()
-        bucket.all_reduce_mean()
+        for _ in range(2):                                      # second step: re-armed by zero_()
+            bucket.zero_()
+            out = model(src[idx], pos[idx], cfg.shapes, ss, lsi)
+            out.square().mean().backward()
+            bucket.finish()
         torch.cuda.synchronize()
+        assert not overlap or bucket.n_slices > 4
         q.put((rank, bucket.flat.cpu()))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_gradients_equal_single_gpu():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_gpu_gradients_equal_single_gpu(overlap):
     import torch.multiprocessing as mp
     from uninext_b200.dp import FlatGradBucket
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() + 13 * int(overlap)) % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=300) for _ in procs)

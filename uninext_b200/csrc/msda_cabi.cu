@@ -614,6 +614,22 @@ int msda_colsum_f32(const float *x, int64_t rows, int cols, float *out, void *st
     return (int)cudaGetLastError();
 }
 
+int msda_relu_backward_colsum_f32(const float *g, const float *y, int64_t rows, int cols, float *g2, float *colsum, void *stream) {
+    if (!g || !y || !g2 || !colsum || rows <= 0 || cols <= 0 || cols % 4 != 0 || !aligned16(g) || !aligned16(y) || !aligned16(g2) ||
+        !aligned16(colsum))
+        return MSDA_E_BADARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, st);
+    if (err != cudaSuccess) return (int)err;
+    long long ctas = (long long)num_sms() * 8;
+    int rows_per_cta = (int)((rows + ctas - 1) / ctas);
+    if (rows_per_cta < 16) rows_per_cta = 16;
+    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    msda::msda_relu_bwd_colsum<<<grid, 256, 0, st>>>(g, y, rows, cols, rows_per_cta, g2, colsum);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int msda_add_layernorm_forward_f32(const float *a, const float *b, const float *gamma, const float *beta, int64_t rows,
                                    int cols, float eps, float *z, float *y, float *mean, float *rstd, void *stream) {
     if (!a || !gamma || !beta || !y || !mean || !rstd || rows <= 0 || (b != nullptr && z == nullptr)) return MSDA_E_BADARG;

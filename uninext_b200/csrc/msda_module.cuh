@@ -134,6 +134,48 @@ msda_colsum(const float *__restrict__ x, long long rows, int cols, int rows_per_
     }
 }
 
+// ReLU backward fused with the bias gradient of the Linear in front of it (FFN linear1, deformable_transformer.py:345-349):
+//   g2[r, c] = y[r, c] > 0 ? g[r, c] : 0 ;   out[c] += sum_r g2[r, c]
+// One pass over g and y instead of threshold_backward followed by a separate column-sum read of g2 (366 MB at cfg2).
+__global__ void __launch_bounds__(256)
+msda_relu_bwd_colsum(const float *__restrict__ g, const float *__restrict__ y, long long rows, int cols, int rows_per_cta,
+                     float *__restrict__ g2, float *__restrict__ out)
+{
+    __shared__ float4 part[256];
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min(rows, r0 + rows_per_cta);
+    const int c4 = cols / 4;
+    const int cs = min(c4, (int)blockDim.x);
+    const int RL = blockDim.x / cs;
+    const int ct = threadIdx.x % cs, rl = threadIdx.x / cs;
+    for (int cb = 0; cb < c4; cb += cs) {
+        const int c = cb + ct;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < RL && c < c4) {
+            long long i = (r0 + rl) * c4 + c;
+#pragma unroll 4
+            for (long long r = r0 + rl; r < r1; r += RL, i += (long long)RL * c4) {
+                const float4 gv = __ldg(reinterpret_cast<const float4 *>(g) + i);
+                const float4 yv = __ldg(reinterpret_cast<const float4 *>(y) + i);
+                const float4 o = make_float4(yv.x > 0.f ? gv.x : 0.f, yv.y > 0.f ? gv.y : 0.f, yv.z > 0.f ? gv.z : 0.f,
+                                             yv.w > 0.f ? gv.w : 0.f);
+                reinterpret_cast<float4 *>(g2)[i] = o;
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        if (rl == 0 && c < c4) {
+            for (int k = 1; k < RL; ++k) {
+                const float4 t = part[k * cs + ct];
+                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+            red_add_v4(out + 4 * c, acc.x, acc.y, acc.z, acc.w);
+        }
+        __syncthreads();
+    }
+}
+
 // z = a + b (b may be null);  y = (z - mean) * rstd * gamma + beta, one warp per row of C = 128*V channels.
 template <int V>
 __global__ void __launch_bounds__(256)

@@ -143,7 +143,18 @@ class _LinearColsum(Function):
     def backward(ctx, g):
         x2, weight, y, mask = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
-        if ctx.relu:
+        gb = None
+        if ctx.relu and g2.is_cuda and g2.dtype == torch.float32 and g2.shape[1] % 4 == 0 and ctx.needs_input_grad[2]:
+            # ReLU backward and the bias gradient in ONE pass over (g, y)  (masked rows have y == 0: zeroed by the same test)
+            g2 = g2.contiguous()
+            out = torch.empty_like(g2)
+            gb = torch.empty(g2.shape[1], dtype=torch.float32, device=g2.device)
+            with torch.cuda.device(g2.device):
+                _cabi.check(_cabi.load().msda_relu_backward_colsum_f32(g2.data_ptr(), y.data_ptr(), g2.shape[0], g2.shape[1],
+                                                                       out.data_ptr(), gb.data_ptr(), _stream()),
+                            "msda_relu_backward_colsum_f32")
+            g2 = out
+        elif ctx.relu:
             g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)          # masked rows have y == 0: already zeroed
         elif mask is not None:
             g2 = g2.masked_fill(mask[:, None], 0.0)
@@ -151,7 +162,8 @@ class _LinearColsum(Function):
             g2 = g2.contiguous()
         gx = torch.mm(g2, weight).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         gw = weight_grad(g2, x2) if ctx.needs_input_grad[1] else None
-        gb = colsum(g2) if ctx.needs_input_grad[2] else None
+        if gb is None and ctx.needs_input_grad[2]:
+            gb = colsum(g2)
         return gx, gw, gb, None, None, None
 
 
