@@ -439,17 +439,12 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
     torch.backends.cuda.matmul.allow_tf32 = True
     overlap_was, bucket.overlap = bucket.overlap, False        # no collectives inside the captured graph
     try:
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                bucket.zero_()
-                model(src, pos, shapes, ss, lsi).float().square().mean().backward()
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        from uninext_b200.graphs import GraphedStep
+
+        def captured():
             bucket.zero_()
             model(src, pos, shapes, ss, lsi).float().square().mean().backward()
+        graph = GraphedStep(captured, warmup=3, device=device)
 
         def graphed_step(_amp):
             graph.replay()
