@@ -149,6 +149,24 @@ int msda_layernorm_backward_f32(const float *dy, const float *z, const float *ga
                                 const float *rstd, int64_t rows, int cols, float *dz, float *dgamma, float *dbeta,
                                 void *stream);
 
+/* ---- geometry feeding the op (deformable_transformer_dino.py:132-171,289-301,612-646): one launch each
+ *   msda_valid_counts:            mask [N, S] bytes (non-zero = padded) -> counts [N, L, 2] int32 = (valid_W, valid_H)  (get_valid_ratio)
+ *   msda_encoder_ref_points_f32:  valid_ratios [N, L, 2] -> reference points [N, S, L, 2]                          (get_reference_points)
+ *   msda_encoder_proposals_f32:   mask + counts -> proposals [N, S, 4] in logit space (+inf = dropped), keep [N, S] bytes
+ *                                 (the geometry half of gen_encoder_output_proposals)
+ *   msda_sine_pos_embed_forward/backward_f32: pos [R, n] -> [R, n * F]                                              (get_sine_pos_embed) */
+int msda_valid_counts(const uint8_t *mask, const int64_t *spatial_shapes, const int64_t *level_start_index, int N, int S, int L,
+                      int32_t *counts, void *stream);
+int msda_encoder_ref_points_f32(const float *valid_ratios, const int64_t *spatial_shapes, const int64_t *level_start_index, int N,
+                                int S, int L, float *ref, void *stream);
+int msda_encoder_proposals_f32(const uint8_t *mask, const int32_t *counts, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, int N, int S, int L, float base_scale, float *proposals,
+                               uint8_t *keep, void *stream);
+int msda_sine_pos_embed_forward_f32(const float *pos, int64_t R, int n, int F, float temperature, int exchange_xy, float *out,
+                                    void *stream);
+int msda_sine_pos_embed_backward_f32(const float *pos, const float *grad_out, int64_t R, int n, int F, float temperature,
+                                     int exchange_xy, float *grad_pos, void *stream);
+
 /* ---- CondInst dynamic mask head (uninext/models/ddetrs.py:488-598, 895-958) ----------------
  * msda_condinst_forward_f32: logits[i, y, x] = MLP_i(rel_x, rel_y, feats[b(i), :, y, x]) for every selected instance i --
  *   the reference's three grouped 1x1 convolutions (groups = #instances, `mask_heads_forward`) over a materialised

@@ -251,3 +251,51 @@ def test_layers_run_fp32_under_autocast_like_reference(ref):
     assert got.dtype == torch.float32
     assert _rel(got, layer(src.bfloat16().float(), pos, refpts, ss, lsi, None)) < 1e-5
     assert _rel(got, want) < 2e-2            # only the bf16 rounding of the input separates them
+
+
+def test_geometry_kernels_match_reference_functions(ref):
+    """f-3 on the GPU: reference points, two-stage proposals and the sine position embedding as single kernels against the
+    reference's own functions (deformable_transformer_dino.py:132-171,289-301,612-646) run on the same device."""
+    from uninext_b200.modules.deformable_transformer import gen_encoder_output_proposals, get_sine_pos_embed
+    dino = ref[3]
+    g = torch.Generator().manual_seed(90)
+    n = 3
+    ss, lsi, masks, flat, src, _ = _pyramid_inputs(n, g)
+    holder = dino.DeformableTransformerVLDINO.__new__(dino.DeformableTransformerVLDINO)
+    want_vr = torch.stack([dino.DeformableTransformerVLDINO.get_valid_ratio(holder, m) for m in masks], 1)
+    lib = _cabi.load()
+    n0 = lib.msda_launch_count()
+    got = get_reference_points(ss, want_vr)
+    assert lib.msda_launch_count() - n0 == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = dino.DeformableTransformerEncoderVL.get_reference_points(ss, want_vr, device=DEV)
+    assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc_output = torch.nn.Linear(256, 256)
+            self.enc_output_norm = torch.nn.LayerNorm(256)
+    h = Holder().to(DEV)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_mem, want_prop = dino.DeformableTransformerVLDINO.gen_encoder_output_proposals(h, src, flat, ss)
+    n0 = lib.msda_launch_count()
+    prop, keep = gen_encoder_output_proposals(flat, ss)
+    assert lib.msda_launch_count() - n0 == 2
+    assert torch.equal(torch.isinf(prop), torch.isinf(want_prop))
+    fin = ~torch.isinf(want_prop)
+    assert torch.allclose(prop[fin], want_prop[fin], rtol=1e-5, atol=1e-5)
+    got_mem = h.enc_output_norm(h.enc_output(src.masked_fill(~keep, 0.0)))
+    assert torch.allclose(got_mem, want_mem, rtol=1e-4, atol=1e-5)
+
+    pos = torch.rand(2, 19, 4, generator=g).to(DEV)
+    a = pos.clone().requires_grad_(True)
+    b = pos.clone().requires_grad_(True)
+    ya, yb = get_sine_pos_embed(a), dino.get_sine_pos_embed(b)
+    assert ya.shape == yb.shape and torch.allclose(ya, yb, rtol=0, atol=2e-5)
+    go = torch.randn(yb.shape, generator=g).to(DEV)
+    ya.backward(go); yb.backward(go)
+    assert _rel(a.grad, b.grad) < 1e-4
+    assert torch.allclose(get_sine_pos_embed(pos[..., :2], 64, 20, False), dino.get_sine_pos_embed(pos[..., :2], 64, 20, False), atol=2e-5)

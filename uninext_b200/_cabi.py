@@ -37,6 +37,11 @@ SIGNATURES = {
     "msda_linear_tf32": (_i, [_vp] * 3 + [ctypes.c_int64, _i, _i, _vp, _vp]),
     "msda_linear_tf32_ex": (_i, [_vp] * 4 + [ctypes.c_int64, _i, _i, _i, _vp, _vp]),
     "msda_linear_tf32_ws_ok": (_i, [_i, _i]),
+    "msda_valid_counts": (_i, [_vp] * 3 + [_i] * 3 + [_vp, _vp]),
+    "msda_encoder_ref_points_f32": (_i, [_vp] * 3 + [_i] * 3 + [_vp, _vp]),
+    "msda_encoder_proposals_f32": (_i, [_vp] * 4 + [_i] * 3 + [ctypes.c_float, _vp, _vp, _vp]),
+    "msda_sine_pos_embed_forward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, ctypes.c_float, _i, _vp, _vp]),
+    "msda_sine_pos_embed_backward_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, ctypes.c_float, _i, _vp, _vp]),
     "msda_condinst_forward_f32": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _vp]),
     "msda_condinst_backward_f32": (_i, [_vp] * 5 + [_i] * 6 + [_vp] * 4),
     "msda_aligned_bilinear_forward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, _i, _vp, _vp]),

@@ -735,3 +735,61 @@ int msda_aligned_bilinear_backward_f32(const float *grad_out, int64_t planes, in
 }
 
 }  // extern "C"
+
+// ---- geometry feeding the op (f-3) --------------------------------------------------------------------------------------
+extern "C" {
+
+int msda_valid_counts(const uint8_t *mask, const int64_t *spatial_shapes, const int64_t *level_start_index, int N, int S, int L,
+                      int32_t *counts, void *stream) {
+    if (!mask || !spatial_shapes || !level_start_index || !counts || N <= 0 || S <= 0 || L <= 0) return MSDA_E_BADARG;
+    const int warps = N * L;
+    msda::msda_valid_counts<<<(warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, spatial_shapes,
+                                                                                                      level_start_index, N, S, L, counts);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_encoder_ref_points_f32(const float *valid_ratios, const int64_t *spatial_shapes, const int64_t *level_start_index, int N,
+                                int S, int L, float *ref, void *stream) {
+    if (!valid_ratios || !spatial_shapes || !level_start_index || !ref || N <= 0 || S <= 0 || L <= 0 || !aligned16(ref)) return MSDA_E_BADARG;
+    const long long total = (long long)N * S;
+    msda::msda_encoder_ref_points<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        valid_ratios, spatial_shapes, level_start_index, N, S, L, ref);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_encoder_proposals_f32(const uint8_t *mask, const int32_t *counts, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, int N, int S, int L, float base_scale, float *proposals,
+                               uint8_t *keep, void *stream) {
+    if (!mask || !counts || !spatial_shapes || !level_start_index || !proposals || !keep || N <= 0 || S <= 0 || L <= 0 || L > 30 ||
+        !aligned16(proposals))
+        return MSDA_E_BADARG;
+    const long long total = (long long)N * S;
+    msda::msda_encoder_proposals<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask, counts, spatial_shapes, level_start_index, N, S, L, base_scale, proposals, keep);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_sine_pos_embed_forward_f32(const float *pos, int64_t R, int n, int F, float temperature, int exchange_xy, float *out,
+                                    void *stream) {
+    if (!pos || !out || R <= 0 || n <= 0 || F <= 0) return MSDA_E_BADARG;
+    const long long warps = (long long)R * n;
+    msda::msda_sine_pos_embed<false><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pos, nullptr, R, n, F, temperature, exchange_xy, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int msda_sine_pos_embed_backward_f32(const float *pos, const float *grad_out, int64_t R, int n, int F, float temperature,
+                                     int exchange_xy, float *grad_pos, void *stream) {
+    if (!pos || !grad_out || !grad_pos || R <= 0 || n <= 0 || F <= 0) return MSDA_E_BADARG;
+    const long long warps = (long long)R * n;
+    msda::msda_sine_pos_embed<true><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        pos, grad_out, R, n, F, temperature, exchange_xy, grad_pos);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

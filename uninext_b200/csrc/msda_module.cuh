@@ -176,6 +176,113 @@ msda_relu_bwd_colsum(const float *__restrict__ g, const float *__restrict__ y, l
     }
 }
 
+// ---- geometry feeding the op (deformable_transformer_dino.py:132-171,289-301,612-646) -----------------
+// The reference builds these with ~20 small PyTorch kernels per forward (meshgrid / linspace / cat / stack per level, with a
+// device->host sync for every level shape).  Here: one launch each, level table read on the device.
+
+// counts[n, l] = (valid_W, valid_H): un-padded extent of level l in image n, from the flattened padding mask
+// (get_valid_ratio, _dino.py:164-171: first row / first column of the level's mask).  One warp per (n, l).
+__global__ void __launch_bounds__(256)
+msda_valid_counts(const unsigned char *__restrict__ mask, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                  int N, int S, int L, int *__restrict__ counts)
+{
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= N * L) return;
+    const int n = gw / L, l = gw - n * L;
+    const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+    const unsigned char *m = mask + (size_t)n * S + (int)lsi[l];
+    int vw = 0, vh = 0;
+    for (int x = lane; x < W; x += 32) vw += m[x] == 0;                 // ~mask[:, 0, :]
+    for (int y = lane; y < H; y += 32) vh += m[(size_t)y * W] == 0;     // ~mask[:, :, 0]
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { vw += __shfl_xor_sync(kFullMask, vw, d); vh += __shfl_xor_sync(kFullMask, vh, d); }
+    if (lane == 0) { counts[2 * gw] = vw; counts[2 * gw + 1] = vh; }
+}
+
+__device__ __forceinline__ int level_of(const int64_t *lsi, const int64_t *shapes, int L, int s, int &x, int &y, int &H, int &W) {
+    int l = 0;
+    while (l + 1 < L && s >= (int)lsi[l + 1]) ++l;
+    H = (int)shapes[2 * l]; W = (int)shapes[2 * l + 1];
+    const int p = s - (int)lsi[l];
+    y = p / W; x = p - y * W;
+    return l;
+}
+
+// ref[n, s, l, :] = ((x + 0.5) / (vr[n, ls, 0] * W), (y + 0.5) / (vr[n, ls, 1] * H)) * vr[n, l, :]   (_dino.py:289-301), ls = level of s
+__global__ void __launch_bounds__(256)
+msda_encoder_ref_points(const float *__restrict__ vr, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+                        int N, int S, int L, float *__restrict__ ref)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N * S) return;
+    const int n = (int)(t / S), s = (int)(t - (long long)n * S);
+    int x, y, H, W;
+    const int ls = level_of(lsi, shapes, L, s, x, y, H, W);
+    const float *v = vr + (size_t)n * L * 2;
+    const float rx = ((float)x + 0.5f) / (v[2 * ls] * (float)W), ry = ((float)y + 0.5f) / (v[2 * ls + 1] * (float)H);
+    float2 *o = reinterpret_cast<float2 *>(ref) + (size_t)t * L;
+    for (int l = 0; l < L; ++l) o[l] = make_float2(rx * v[2 * l], ry * v[2 * l + 1]);
+}
+
+// Two-stage proposals (_dino.py:132-156): prop = logit((x+.5)/valid_W, (y+.5)/valid_H, 0.05*2^l, 0.05*2^l), +inf where the
+// position is padded or any coordinate is outside (0.01, 0.99); keep = position survives.
+__global__ void __launch_bounds__(256)
+msda_encoder_proposals(const unsigned char *__restrict__ mask, const int *__restrict__ counts, const int64_t *__restrict__ shapes,
+                       const int64_t *__restrict__ lsi, int N, int S, int L, float base_scale, float *__restrict__ prop,
+                       unsigned char *__restrict__ keep)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)N * S) return;
+    const int n = (int)(t / S), s = (int)(t - (long long)n * S);
+    int x, y, H, W;
+    const int l = level_of(lsi, shapes, L, s, x, y, H, W);
+    const int *c = counts + ((size_t)n * L + l) * 2;
+    const float wh = base_scale * (float)(1 << l);
+    const float p[4] = {((float)x + 0.5f) / (float)c[0], ((float)y + 0.5f) / (float)c[1], wh, wh};
+    bool ok = mask[t] == 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ok = ok && p[i] > 0.01f && p[i] < 0.99f;
+    float4 o;
+    const float inf = __int_as_float(0x7f800000);
+    o.x = ok ? logf(p[0] / (1.f - p[0])) : inf; o.y = ok ? logf(p[1] / (1.f - p[1])) : inf;
+    o.z = ok ? logf(p[2] / (1.f - p[2])) : inf; o.w = ok ? logf(p[3] / (1.f - p[3])) : inf;
+    reinterpret_cast<float4 *>(prop)[t] = o;
+    keep[t] = ok ? 1 : 0;
+}
+
+// Sine position embedding of box coordinates (get_sine_pos_embed, _dino.py:612-646): out[r, slot(k) * F + j] =
+// sin / cos (j even / odd) of pos[r, k] * 2 pi / T^(2 (j / 2) / F); slot swaps components 0 and 1 when exchange_xy.
+// BWD: grad_pos[r, k] = sum_j g * d/dpos (one warp per (r, k)).
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+msda_sine_pos_embed(const float *__restrict__ pos, const float *__restrict__ gout, long long R, int n, int F, float temperature,
+                    int exchange_xy, float *__restrict__ out)
+{
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= R * n) return;
+    const long long r = gw / n;
+    const int k = (int)(gw - r * n);
+    const int slot = (exchange_xy && n >= 2 && k < 2) ? 1 - k : k;
+    const float p = pos[gw] * 6.283185307179586f;
+    float acc = 0.f;
+    for (int j = lane; j < F; j += 32) {
+        const float dim_t = powf(temperature, (float)(2 * (j / 2)) / (float)F);
+        const float a = p / dim_t;
+        if (!BWD) {
+            out[(r * n + slot) * F + j] = (j & 1) ? cosf(a) : sinf(a);
+        } else {
+            const float g = gout[(r * n + slot) * F + j];
+            acc += g * ((j & 1) ? -sinf(a) : cosf(a)) * (6.283185307179586f / dim_t);
+        }
+    }
+    if (BWD) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
+        if (lane == 0) out[gw] = acc;
+    }
+}
+
 // z = a + b (b may be null);  y = (z - mean) * rstd * gamma + beta, one warp per row of C = 128*V channels.
 template <int V>
 __global__ void __launch_bounds__(256)

@@ -50,11 +50,47 @@ class MLP(nn.Module):
         return x
 
 
+class _SinePosEmbed(torch.autograd.Function):
+    """get_sine_pos_embed as one kernel per direction (msda_sine_pos_embed_forward/backward_f32)."""
+
+    @staticmethod
+    def forward(ctx, pos, num_pos_feats, temperature, exchange_xy):
+        from uninext_b200 import _cabi
+        lib = _cabi.load()
+        p2 = pos.contiguous().float()
+        n = p2.shape[-1]
+        r = p2.numel() // n
+        out = torch.empty((*p2.shape[:-1], n * num_pos_feats), dtype=torch.float32, device=pos.device)
+        with torch.cuda.device(pos.device):
+            _cabi.check(lib.msda_sine_pos_embed_forward_f32(p2.data_ptr(), r, n, num_pos_feats, float(temperature), int(exchange_xy),
+                                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "msda_sine_pos_embed_forward_f32")
+        ctx.save_for_backward(p2)
+        ctx.cfg = (r, n, num_pos_feats, float(temperature), int(exchange_xy), pos.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from uninext_b200 import _cabi
+        lib = _cabi.load()
+        (p2,) = ctx.saved_tensors
+        r, n, f, t, xy, dt = ctx.cfg
+        g = g.contiguous().float()
+        gp = torch.empty_like(p2)
+        with torch.cuda.device(p2.device):
+            _cabi.check(lib.msda_sine_pos_embed_backward_f32(p2.data_ptr(), g.data_ptr(), r, n, f, t, xy, gp.data_ptr(),
+                                                             torch.cuda.current_stream().cuda_stream),
+                        "msda_sine_pos_embed_backward_f32")
+        return gp.to(dt), None, None, None
+
+
 def get_sine_pos_embed(pos_tensor: torch.Tensor, num_pos_feats: int = 128, temperature: int = 10000,
                        exchange_xy: bool = True) -> torch.Tensor:
     """[.., Q, n] positions in [0, 1] -> [.., Q, n * num_pos_feats] sine embedding (deformable_transformer_dino.py:612-646):
     component k, feature j = sin / cos (j even / odd) of ``pos_k * 2*pi / temperature ** (2 * (j // 2) / num_pos_feats)``;
-    with ``exchange_xy`` the y block comes first."""
+    with ``exchange_xy`` the y block comes first.  CUDA tensors: one hand-written kernel per direction."""
+    if pos_tensor.is_cuda and pos_tensor.dtype == torch.float32:
+        return _SinePosEmbed.apply(pos_tensor, int(num_pos_feats), temperature, bool(exchange_xy))
     dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=pos_tensor.device)
     dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
     arg = pos_tensor.unsqueeze(-1) * (2 * math.pi) / dim_t                         # [.., n, F]
@@ -67,7 +103,8 @@ def get_sine_pos_embed(pos_tensor: torch.Tensor, num_pos_feats: int = 128, tempe
 
 def valid_ratios_from_masks(masks):
     """Per level ``(valid_W / W, valid_H / H)`` from the padding masks [N, H_l, W_l] -> [N, L, 2]
-    (get_valid_ratio, deformable_transformer_dino.py:164-171)."""
+    (get_valid_ratio, deformable_transformer_dino.py:164-171).  (With a flattened mask, msda_valid_counts gives the same
+    counts in one launch: see gen_encoder_output_proposals.)"""
     out = []
     for m in masks:
         _, h, w = m.shape
@@ -104,11 +141,37 @@ def _shapes_key(spatial_shapes):
     return tuple((int(h), int(w)) for h, w in spatial_shapes)
 
 
+def _level_args(spatial_shapes, level_start_index, device):
+    """(device [L,2] int64, device [L] int64, S) for the geometry kernels; host values come from the cached shapes key."""
+    key = _shapes_key(spatial_shapes)
+    hit = _LEVEL_TENSORS.get((key, str(device)))
+    if hit is None:
+        ss = torch.as_tensor(key, dtype=torch.long, device=device)
+        lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+        hit = _LEVEL_TENSORS[(key, str(device))] = (ss, lsi, sum(h * w for h, w in key))
+    return hit
+
+
+_LEVEL_TENSORS = {}
+
+
 def get_reference_points(spatial_shapes, valid_ratios, device=None):
     """Encoder reference points [N, S, L, 2] (deformable_transformer_dino.py:289-301): pixel centre of every pyramid
-    position, normalised by the valid extent of ITS level, then scaled by every level's valid ratio.  The pixel grid is
-    a constant of ``spatial_shapes`` and is cached; per call only one divide and one multiply remain."""
+    position, normalised by the valid extent of ITS level, then scaled by every level's valid ratio.  CUDA: one kernel
+    (msda_encoder_ref_points_f32, level table read on the device).  CPU: the pixel grid is a constant of ``spatial_shapes``
+    and is cached; per call only one divide and one multiply remain."""
     device = device or valid_ratios.device
+    if valid_ratios.is_cuda and valid_ratios.dtype == torch.float32 and not valid_ratios.requires_grad:
+        from uninext_b200 import _cabi
+        ss, lsi, s_total = _level_args(spatial_shapes, None, valid_ratios.device)
+        n, l = valid_ratios.shape[0], ss.shape[0]
+        vr = valid_ratios.contiguous()
+        ref = torch.empty((n, s_total, l, 2), dtype=torch.float32, device=vr.device)
+        with torch.cuda.device(vr.device):
+            _cabi.check(_cabi.load().msda_encoder_ref_points_f32(vr.data_ptr(), ss.data_ptr(), lsi.data_ptr(), n, s_total, l,
+                                                                 ref.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "msda_encoder_ref_points_f32")
+        return ref
     xy, wh, lvl = _pixel_centres(_shapes_key(spatial_shapes), device)
     ref = xy[None] / (valid_ratios[:, lvl] * wh[None])                  # [N, S, 2]
     return ref[:, :, None] * valid_ratios[:, None]
@@ -122,6 +185,23 @@ def gen_encoder_output_proposals(memory_padding_mask, spatial_shapes, base_scale
     shapes = _shapes_key(spatial_shapes)
     n = memory_padding_mask.shape[0]
     device = memory_padding_mask.device
+    if memory_padding_mask.is_cuda:                 # two launches: valid extents per (image, level), then the proposals
+        from uninext_b200 import _cabi
+        lib = _cabi.load()
+        ss, lsi, s_total = _level_args(spatial_shapes, None, device)
+        l = ss.shape[0]
+        m8 = memory_padding_mask.to(torch.uint8).contiguous()
+        counts = torch.empty((n, l, 2), dtype=torch.int32, device=device)
+        prop = torch.empty((n, s_total, 4), dtype=torch.float32, device=device)
+        keep = torch.empty((n, s_total, 1), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.msda_valid_counts(m8.data_ptr(), ss.data_ptr(), lsi.data_ptr(), n, s_total, l, counts.data_ptr(), st),
+                        "msda_valid_counts")
+            _cabi.check(lib.msda_encoder_proposals_f32(m8.data_ptr(), counts.data_ptr(), ss.data_ptr(), lsi.data_ptr(), n, s_total,
+                                                       l, float(base_scale), prop.data_ptr(), keep.data_ptr(), st),
+                        "msda_encoder_proposals_f32")
+        return prop, keep.bool()
     xy, wh, lvl = _pixel_centres(shapes, device)
     counts, cur = [], 0
     for h, w in shapes:
