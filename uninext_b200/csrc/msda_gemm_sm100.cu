@@ -314,7 +314,7 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             mbar_expect_tx(&w_bar, (unsigned)KB * wk_bytes);
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(w_res + (size_t)kb * wk_bytes, &map_w, kb * BLOCK_K, (int)rank * NH, &w_bar);
-            unsigned it = 0;
+            unsigned it = 0, s = 0, ph = 0;
             // The ring holds only 4-5 A stages next to the resident W (64-80 KB in flight per SM), too little to cover the
             // DRAM latency of a tile load: each CTA therefore prefetches ITS half of the NEXT tile into L2 (no smem, no
             // barrier) while the current tile streams, so that the ring's loads are L2 hits.
@@ -326,7 +326,6 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     for (int kb = 0; kb < KB; ++kb)
                         tma_prefetch_2d(&map_a, kb * BLOCK_K, (int)((t + tile_stride) * BLOCK_M) + (int)rank * (BLOCK_M / 2));
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);                    // the MMAs (of both CTAs when sharing) have drained it
                     mbar_expect_tx(&full_bar[s], a_bytes);               // whole tile: own half + the peer's half, or own copy
                     if (p.multicast)
@@ -334,6 +333,7 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                        &full_bar[s], (uint16_t)3);
                     else
                         tma_load_2d(stages + (size_t)s * a_bytes, &map_a_full, kb * BLOCK_K, (int)(t * BLOCK_M), &full_bar[s]);
+                    if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -342,26 +342,30 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_wait(&w_bar, 0);
         unsigned it = 0, tt = 0;
         const uint32_t idesc = umma_idesc_tf32(BLOCK_M, NH);
+        // The issuing lane is ONE thread: everything it executes per MMA is on the critical path of the tensor pipe.  The
+        // descriptors are therefore built once; per MMA only their address field (bits 0-13, units of 16 bytes) is bumped.
+        const uint64_t a_desc0 = umma_desc(stages, 0), w_desc0 = umma_desc(w_res, 0);
+        const uint32_t a_step = a_bytes >> 4, w_step = wk_bytes >> 4, k_step = (UMMA_K * 4) >> 4;
+        unsigned s = 0, ph = 0;                                          // ring position of `it` without div / mod
         for (long long t = tile0; t < ntiles; t += tile_stride, ++tt) {
             const unsigned buf = tt & 1, use = tt >> 1;
             mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_base + buf * (uint32_t)NH;
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const unsigned char *sa = stages + (size_t)s * a_bytes;
-                    const unsigned char *sw = w_res + (size_t)kb * wk_bytes;
+                    const uint64_t ad = a_desc0 + (uint64_t)(s * a_step), wd = w_desc0 + (uint64_t)((unsigned)kb * w_step);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_tf32(acc, umma_desc(sa, k * UMMA_K * 4), umma_desc(sw, k * UMMA_K * 4), idesc, (kb | k) != 0);
+                        umma_tf32(acc, ad + (uint64_t)(k * k_step), wd + (uint64_t)(k * k_step), idesc, (kb | k) != 0);
                     if (p.multicast) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // free in BOTH CTAs once both have committed
                     else umma_commit(&empty_bar[s]);
                     if (kb == KB - 1) umma_commit(&tmem_full_bar[buf]);
                 }
                 __syncwarp();
+                if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
