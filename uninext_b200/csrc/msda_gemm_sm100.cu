@@ -165,48 +165,51 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            unsigned it = 0;                                             // global k-block counter across tiles
+            unsigned s = 0, ph = 0;                                      // ring position across tiles (no div / mod)
             const int half = N / 2;                                      // rows of W this CTA loads and multicasts
             for (long long pr = pair0; pr < npairs; pr += pair_stride) {
                 const int row0 = (int)((pr * 2 + rank) * BLOCK_M);       // may lie beyond M for the last pair: TMA zero-fills
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
+                for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);                    // both CTAs have drained this stage
                     unsigned char *sa = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_bar[s], stage_bytes);           // own A tile + both halves of W
                     tma_load_2d(sa, &map_a, kb * BLOCK_K, row0, &full_bar[s]);
                     tma_load_2d_mc(sa + a_bytes + (size_t)rank * half * BLOCK_K * 4, &map_w, kb * BLOCK_K, (int)rank * half,
                                    &full_bar[s], (uint16_t)3);
+                    if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        unsigned it = 0, t = 0;
+        unsigned it = 0, t = 0, s = 0, ph = 0;
+        // one thread issues every MMA: descriptors are built once, per MMA only their 16-byte-unit address field moves
+        const uint64_t a_desc0 = umma_desc(smem, 0), w_desc0 = umma_desc(smem + a_bytes, 0);
+        const uint32_t st_step = stage_bytes >> 4, k_step = (UMMA_K * 4) >> 4, n_step = (256u * BLOCK_K * 4) >> 4;
+        const uint32_t idesc0 = umma_idesc_tf32(BLOCK_M, min(256, N)), idesc1 = N > 256 ? umma_idesc_tf32(BLOCK_M, N - 256) : 0u;
         for (long long pr = pair0; pr < npairs; pr += pair_stride, ++t) {
             const unsigned buf = t % p.acc_bufs, use = t / p.acc_bufs;
             mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);              // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_base + buf * (uint32_t)N;
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const unsigned s = it % p.stages, ph = (it / p.stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const unsigned char *sa = smem + (size_t)s * stage_bytes;
-                    const unsigned char *sw = sa + a_bytes;
-                    for (int n0 = 0; n0 < N; n0 += 256) {
-                        const int nt = min(256, N - n0);
-                        const uint32_t idesc = umma_idesc_tf32(BLOCK_M, nt);
+                    const uint64_t ad = a_desc0 + (uint64_t)(s * st_step), wd = w_desc0 + (uint64_t)(s * st_step);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_tf32(acc, ad + (uint64_t)(k * k_step), wd + (uint64_t)(k * k_step), idesc0, (kb | k) != 0);
+                    if (N > 256) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_tf32(acc + (uint32_t)n0, umma_desc(sa, k * UMMA_K * 4),
-                                      umma_desc(sw + (size_t)n0 * BLOCK_K * 4, k * UMMA_K * 4), idesc, (kb | k) != 0);
+                            umma_tf32(acc + 256u, ad + (uint64_t)(k * k_step), wd + (uint64_t)(n_step + k * k_step), idesc1, (kb | k) != 0);
                     }
                     umma_commit_mc(&empty_bar[s], (uint16_t)3);          // tell both producers this CTA is done with the stage
                     if (kb == KB - 1) umma_commit(&tmem_full_bar[buf]);  // accumulator complete
                 }
                 __syncwarp();
+                if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
