@@ -438,16 +438,19 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 __syncwarp();
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + (size_t)rank * NH + c0 + c4));
+                float4 o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = *reinterpret_cast<const float4 *>(&xp[rr + 4 * i][c4]);     // all loads first
+                __syncwarp();                                            // staging tile free for the next chunk
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const long long r = row_base + rr + 4 * i;
-                    float4 o = *reinterpret_cast<const float4 *>(&xp[rr + 4 * i][c4]);
+                    float4 o = o8[i];
                     o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (dead_bits & (1u << i)) o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < p.M) *reinterpret_cast<float4 *>(p.C + r * (long long)p.N + (long long)rank * NH + c0 + c4) = o;
                 }
-                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0)
