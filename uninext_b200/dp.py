@@ -122,6 +122,10 @@ class FlatGradBucket:
                 v.copy_(p.grad)                      # the aliasing was broken since the last step: repair in place
                 p.grad = v
             k = self._slice_of[i]
+            if self._next < 0 and _distributed(self.group):
+                raise RuntimeError("FlatGradBucket(overlap=True): a gradient arrived after every slice of this step had been "
+                                   "all-reduced -- call zero_() (which re-arms the exchange) before each backward; gradient "
+                                   "accumulation over several backward passes needs overlap=False")
             self._pending[k] -= 1
             self._launch_ready()
         return hook
