@@ -159,7 +159,11 @@ class DeformableStack(nn.Module):
         boxes = self.reference_boxes[None].expand(n, -1, -1)                              # [N, Q, 4] (cx, cy, w, h)
         ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
         out = tgt
-        values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)   # memory is loop-invariant
+        import os
+        if os.environ.get("MSDA_NO_BATCHED_VPROJ") == "1":          # A/B switch for measurements
+            values = [None] * len(self.decoder)
+        else:
+            values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)   # memory is loop-invariant
         for layer, val in zip(self.decoder, values):
             out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None, projected_value=val)
         return out
