@@ -184,11 +184,15 @@ def test_reference_reid_head_on_dropin(ref):
     _compare(ours, theirs, lambda m, t, x: m(t, boxes, x, ss, lsi, vr, None, flat, None), [tgt, src])
 
 
+@pytest.mark.parametrize("batched", [False, True])
 @pytest.mark.parametrize("refine", [True, False])
-def test_reference_decoder_loop_on_dropin(ref, refine):
+def test_reference_decoder_loop_on_dropin(ref, refine, batched):
     """The whole DINO decoder loop (sine embedding -> ref_point_head -> layer -> box refinement, look_forward_twice),
     reference class on the drop-in against this repo's decoder, which projects the memory for all layers in ONE batched
     GEMM."""
+    from uninext_b200.modules.ms_deform_attn import use_batched_value_proj
+    was = use_batched_value_proj()
+    use_batched_value_proj(batched)
     g = torch.Generator().manual_seed(80)
     n, q, nl = 2, 23, 3
     ss, lsi, masks, flat, src, _ = _pyramid_inputs(n, g)
@@ -211,7 +215,10 @@ def test_reference_decoder_loop_on_dropin(ref, refine):
     def run(m, t, x):
         hs, refs = m(t, boxes, x, ss, lsi, vr, None, flat, None)
         return torch.cat((hs.flatten(), refs.flatten()))
-    _compare(ours, theirs, run, [tgt, src])
+    try:
+        _compare(ours, theirs, run, [tgt, src])
+    finally:
+        use_batched_value_proj(was)
 
 
 def test_batched_value_proj_equals_per_layer_projection():

@@ -11,7 +11,7 @@ from torch import nn
 
 from uninext_b200.functions.fused import add_layer_norm, linear_colsum
 
-from .ms_deform_attn import MSDeformAttn, batched_value_proj
+from .ms_deform_attn import MSDeformAttn, batched_value_proj, use_batched_value_proj
 
 
 def _add_pos(x, pos):
@@ -159,11 +159,10 @@ class DeformableStack(nn.Module):
         boxes = self.reference_boxes[None].expand(n, -1, -1)                              # [N, Q, 4] (cx, cy, w, h)
         ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
         out = tgt
-        import os
-        if os.environ.get("MSDA_NO_BATCHED_VPROJ") == "1":          # A/B switch for measurements
-            values = [None] * len(self.decoder)
+        if use_batched_value_proj():                                 # memory is loop-invariant: one [256 -> 6 x 256] GEMM
+            values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)
         else:
-            values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)   # memory is loop-invariant
+            values = [None] * len(self.decoder)
         for layer, val in zip(self.decoder, values):
             out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None, projected_value=val)
         return out

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .deformable_layers import DeformableTransformerDecoderLayer, fp32_under_autocast
-from .ms_deform_attn import batched_value_proj
+from .ms_deform_attn import batched_value_proj, use_batched_value_proj
 
 
 def inverse_sigmoid(x, eps: float = 1e-5):
@@ -28,7 +28,8 @@ def inverse_sigmoid(x, eps: float = 1e-5):
 def _projected_values(layers, src, src_padding_mask):
     """One batched value projection for all layers over the loop-invariant encoder memory, when
     every layer is this repo's decoder layer; None otherwise (each layer then projects for itself)."""
-    if all(isinstance(l, DeformableTransformerDecoderLayer) for l in layers) and src.is_cuda and len(layers) > 1:
+    if use_batched_value_proj() and all(isinstance(l, DeformableTransformerDecoderLayer) for l in layers) and src.is_cuda \
+            and len(layers) > 1:
         return batched_value_proj([l.cross_attn for l in layers], src, src_padding_mask)
     return None
 

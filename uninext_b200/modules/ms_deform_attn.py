@@ -152,6 +152,20 @@ class MSDeformAttn(nn.Module):
                              input_padding_mask, projected_value)
 
 
+# Measured on B200 (profiles/r02q_stack_value_proj_batching.txt): the strided-batched GEMM (shared A, batch = 6) plus its
+# accumulate-in-place backward costs 1.0 ms MORE device time per cfg2 step than six plain cuBLAS GEMMs (15.50 vs 14.46 ms), so
+# the decoder loops use it only on request (MSDA_BATCHED_VPROJ=1 or use_batched_value_proj(True)).
+_BATCHED_VPROJ = __import__("os").environ.get("MSDA_BATCHED_VPROJ") == "1"
+
+
+def use_batched_value_proj(flag=None) -> bool:
+    """Query / set whether the decoder loops project the memory for all layers in one batched GEMM."""
+    global _BATCHED_VPROJ
+    if flag is not None:
+        _BATCHED_VPROJ = bool(flag)
+    return _BATCHED_VPROJ
+
+
 def batched_value_proj(attn_modules, input_flatten, input_padding_mask=None):
     """``[m.value_proj(input_flatten) for m in attn_modules]`` with the padding mask applied, as ONE batched GEMM.
     The decoder's layers (and the ReID head's) all project the SAME encoder memory (deformable_transformer_dino.py:451-475:
