@@ -178,6 +178,8 @@ def run_b200(args):
     device = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on STDOUT: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     lib = _cabi.load()
     cfg = CONFIGS[args.config]
