@@ -72,7 +72,9 @@ uint64_t msda_launch_count(void);
  *   MSDA_KNOB_F32_VEC8_FWD / _BWD   lane shape of the fp32 tiled kernels: 1 = 4 lanes x 32 B per row, 0 = 8 lanes x 16 B
  *   MSDA_KNOB_BF16_FINE_ROWS        msda_backward_bf16 with a bf16 result: levels of at least this many rows accumulate
  *                                   grad_value directly in bf16 (packed 8-byte reds); the others in fp32.  0 = all fp32.
- *                                   (The only knob that changes results: within the 1e-2 bf16 tolerance, see DESIGN.md.) */
+ *                                   (changes results within the 1e-2 bf16 tolerance, see DESIGN.md.)
+ *   MSDA_KNOB_BF16_PACKED_FWD       bf16 forward (D = 32 / 64, large launches): blend the 4 corners of a tap in packed bf16 and
+ *                                   accumulate taps in fp32 (~3 extra bf16 roundings per tap; also changes results slightly). */
 #define MSDA_KNOB_SLAB          0
 #define MSDA_KNOB_BWD_WIN_ROWS  1
 #define MSDA_KNOB_BWD_LIST_CAP  2
@@ -80,7 +82,8 @@ uint64_t msda_launch_count(void);
 #define MSDA_KNOB_F32_VEC8_FWD  4   /* fp32 tiled forward: 8 channels per lane (LDG.256), D in {32, 64}; 0 / 1        */
 #define MSDA_KNOB_F32_VEC8_BWD  5   /* fp32 tiled backward: same lane shape; 0 / 1                                     */
 #define MSDA_KNOB_BF16_FINE_ROWS 6  /* bf16 backward: levels with H*W >= this accumulate grad_value in bf16; 0 = off */
-#define MSDA_KNOB_COUNT         7
+#define MSDA_KNOB_BF16_PACKED_FWD 7 /* bf16 forward: corners of a tap blended in packed bf16 (HFMA2); 0 / 1            */
+#define MSDA_KNOB_COUNT         8
 #define MSDA_KNOB_QUERY         (-1000000)
 int msda_set_knob(int knob, int value);
 

@@ -29,7 +29,7 @@ DEV = "cuda"
 @pytest.fixture
 def knobs():
     lib = _cabi.load()
-    saved = [lib.msda_set_knob(k, -1000000) for k in range(7)]
+    saved = [lib.msda_set_knob(k, -1000000) for k in range(8)]
     yield lib
     for k, v in enumerate(saved):
         lib.msda_set_knob(k, v)
@@ -225,3 +225,18 @@ def test_tmem_and_tiled_backward_agree_at_cfg2(knobs):
     for i, (a, b) in enumerate(zip(got, ref)):
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 2e-5 * scale, i
+
+
+@pytest.mark.parametrize("cfgname", ["cfg1", "cfg4"])
+def test_bf16_forward_packed_corner_blend_vs_oracle(knobs, cfgname):
+    """bf16 forward with the four corners of a tap blended in packed bf16 (HFMA2) and taps accumulated in fp32
+    (MSDA_KNOB_BF16_PACKED_FWD): inside the bf16 tolerance of the fp64 oracle; the error is reported for the record."""
+    inp = make_inputs(CONFIGS[cfgname], "enc", DEV, dtype=torch.bfloat16, seed=47, wild_fraction=0.1)
+    a = (inp["value"], inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"])
+    f64 = lambda t: t.detach().double().cpu().numpy()
+    want = msda_oracle.forward(f64(a[0]), a[1].cpu().numpy(), a[2].cpu().numpy(), f64(a[3]), f64(a[4]))
+    base = _err(MSDA.ms_deform_attn_forward(*a, 64), want)
+    knobs.msda_set_knob(_cabi.KNOB_BF16_PACKED_FWD, 1)
+    packed = _err(MSDA.ms_deform_attn_forward(*a, 64), want)
+    print(f"bf16 forward max err / scale at {cfgname}: fp32 blend {base:.4f}, packed bf16 blend {packed:.4f}")
+    assert base < 1e-2 and packed < 1e-2

@@ -67,6 +67,7 @@ struct Knobs {
         v[MSDA_KNOB_F32_VEC8_FWD].store(env_int("MSDA_F32_VEC8_FWD", 0));
         v[MSDA_KNOB_F32_VEC8_BWD].store(env_int("MSDA_F32_VEC8_BWD", 0));
         v[MSDA_KNOB_BF16_FINE_ROWS].store(env_int("MSDA_BF16_FINE_ROWS", 0));
+        v[MSDA_KNOB_BF16_PACKED_FWD].store(env_int("MSDA_BF16_PACKED_FWD", 0));
     }
 };
 Knobs &knobs() { static Knobs k; return k; }
@@ -150,6 +151,21 @@ cudaError_t launch_fwd(const T *value, const int64_t *shapes, const int64_t *lsi
     const unsigned npairs = (unsigned)((long long)d.N * d.Lq * d.M);
     const bool split = kCanSplit && use_split(npairs);
     const bool tma = !split && kCanStage && use_tma_staging(d);
+    if constexpr (sizeof(T) == 2 && VEC == 8) {      // bf16: packed-bf16 corner blend for the large (non-split) launches
+        if (!split && knob(MSDA_KNOB_BF16_PACKED_FWD) == 1) {
+            static std::atomic<int> c_ptma[kMaxDevices], c_pldg[kMaxDevices];
+            auto k_tma = msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false, true>;
+            auto k_ldg = msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false, true>;
+            const int pslots = tma ? resident_ctas_cached(k_tma, c_ptma) : resident_ctas_cached(k_ldg, c_pldg);
+            const unsigned ip = msda::kTiledWarps * GPW;
+            const unsigned tub = (npairs + ip - 1) / ip;
+            const int pgrid = (int)(tub < (unsigned)pslots ? tub : (unsigned)pslots);
+            (tma ? k_tma : k_ldg)<<<pgrid, msda::kTiledThreads, 0, st>>>(value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
+                                                                          npairs, allow_patches(), out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return cudaGetLastError();
+        }
+    }
     auto kern = split ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, kCanSplit>
                 : tma ? msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, kCanStage, false>
                       : msda::msda_fwd_tiled<T, VEC, D, LP_MAX, kFwdMinCtas, false, false>;

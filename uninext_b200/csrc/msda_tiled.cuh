@@ -183,7 +183,11 @@ __device__ __forceinline__ float4 masked_weights(const TapGeom &g, float a) {
 // ------------------------------------------------------------------------------------------------------------
 // forward:  out[b,q,m,:] = sum_taps a * bilinear(value_l[b,:,m,:], x, y)            (reference cuh:237-299)
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT>
+// PACKED (bf16 storage, VEC = 8 only): the four corners of a tap are blended in packed bf16 (one HMUL2 + three HFMA2 per
+// 2 channels, corner weights broadcast as bf16x2 in the tap record) and only the blended tap is widened and accumulated in
+// fp32 -- 4 packed ops + 2 widen + 2 adds per word instead of 8 widen + 8 FFMA.  The bf16 forward is issue-bound on exactly
+// that unpack / FFMA stream (smsp__issue_active 68 %, profiles/r01k_enc_bf16_ncu.md).  Costs ~3 bf16 roundings per tap.
+template <typename T, int VEC, int D, int LP_MAX, int MIN_CTAS, bool TMA, bool SPLIT, bool PACKED = false>
 __global__ void __launch_bounds__(kTiledThreads, MIN_CTAS)
 msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn,
@@ -201,6 +205,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     static_assert(D % VEC == 0 && (LPR & (LPR - 1)) == 0 && LPR <= 32 && LP_MAX % LPR == 0, "bad tiling");
     static_assert(SPLIT || (kTileSlots % (kTiledWarps * GPW) == 0 && ITERS >= 1), "tile must be whole iterations");
     static_assert(!SPLIT || (LP_MAX % GPW == 0 && LP_MAX / GPW <= LPR && !TMA), "SPLIT: one record round, LDG taps");
+    static_assert(!PACKED || (sizeof(T) == 2 && VEC == 8), "PACKED blends bf16 rows, 8 channels (one 16-byte load) per lane");
 
     __shared__ WorkMap wm;
     __shared__ __align__(16) unsigned char slab_mem[kTiledWarps * TapSlab<LPR>::kBytes];
@@ -273,6 +278,14 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                     const int l = s / P;
                     const TapGeom g = tap_geometry(xy.x, xy.y, wm.H[l], wm.W[l], wm.start[l]);
                     tw[k] = masked_weights(g, a);
+                    if constexpr (PACKED) {            // record carries each corner weight as a broadcast bf16x2 pattern
+                        const __nv_bfloat162 a2 = __floats2bfloat162_rn(tw[k].x, tw[k].x), b2 = __floats2bfloat162_rn(tw[k].y, tw[k].y),
+                                             c2 = __floats2bfloat162_rn(tw[k].z, tw[k].z), d2 = __floats2bfloat162_rn(tw[k].w, tw[k].w);
+                        tw[k] = make_float4(__uint_as_float(*reinterpret_cast<const unsigned *>(&a2)),
+                                            __uint_as_float(*reinterpret_cast<const unsigned *>(&b2)),
+                                            __uint_as_float(*reinterpret_cast<const unsigned *>(&c2)),
+                                            __uint_as_float(*reinterpret_cast<const unsigned *>(&d2)));
+                    }
                     tr[k] = make_int2(g.r0, g.r1 | (g.dw << 31));
                 }
             }
@@ -295,6 +308,25 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                     const unsigned dwo = (rr.y < 0) ? row_bytes : 0u;
                     const unsigned char *p0 = base + (unsigned long long)(unsigned)rr.x * row_bytes;
                     const unsigned char *p1 = base + (unsigned long long)(unsigned)(rr.y & 0x7fffffff) * row_bytes;
+                    if constexpr (PACKED) {
+                        const uint4 q00 = __ldg(reinterpret_cast<const uint4 *>(p0)), q01 = __ldg(reinterpret_cast<const uint4 *>(p0 + dwo));
+                        const uint4 q10 = __ldg(reinterpret_cast<const uint4 *>(p1)), q11 = __ldg(reinterpret_cast<const uint4 *>(p1 + dwo));
+                        const unsigned u00[4] = {q00.x, q00.y, q00.z, q00.w}, u01[4] = {q01.x, q01.y, q01.z, q01.w};
+                        const unsigned u10[4] = {q10.x, q10.y, q10.z, q10.w}, u11[4] = {q11.x, q11.y, q11.z, q11.w};
+                        const unsigned wx = __float_as_uint(w.x), wy = __float_as_uint(w.y), wz = __float_as_uint(w.z),
+                                       ww = __float_as_uint(w.w);
+                        auto b2 = [](unsigned u) { return *reinterpret_cast<const __nv_bfloat162 *>(&u); };
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 t = __hmul2(b2(wx), b2(u00[i]));
+                            t = __hfma2(b2(wy), b2(u01[i]), t);
+                            t = __hfma2(b2(wz), b2(u10[i]), t);
+                            t = __hfma2(b2(ww), b2(u11[i]), t);
+                            const unsigned tu = *reinterpret_cast<const unsigned *>(&t);
+                            acc[2 * i] += __uint_as_float(tu << 16);
+                            acc[2 * i + 1] += __uint_as_float(tu & 0xffff0000u);
+                        }
+                    } else {
                     float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
                     RowVec<T, VEC>::load(reinterpret_cast<const T *>(p0), v00);
                     RowVec<T, VEC>::load(reinterpret_cast<const T *>(p0 + dwo), v01);
@@ -306,6 +338,7 @@ msda_fwd_tiled(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
                         acc[e] = fmaf(w.y, v01[e], acc[e]);
                         acc[e] = fmaf(w.z, v10[e], acc[e]);
                         acc[e] = fmaf(w.w, v11[e], acc[e]);
+                    }
                     }
                 }
             }
