@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2   /* 2: round-2 entry points (knobs, CondInst head, geometry, W-stationary GEMM) */
 
 #define MSDA_E_BADARG   (-1)   /* null pointer, non-positive dimension, unknown knob                  */
 #define MSDA_E_TOOLARGE (-2)   /* a dimension product exceeds what the kernels index (see msda_b200.h) */
@@ -179,15 +179,15 @@ int msda_sine_pos_embed_backward_f32(const float *pos, const float *grad_out, in
  *     [inst_start[b], inst_start[b+1]); max_inst = largest per-image count (host value, sizes the grid);
  *     stride = mask_feat_stride; rel_coord = 1 prepends (ref - pixel location) as two input channels, 0 feeds zeros;
  *     logits [I, H, W].
- * msda_condinst_backward_f32: grad_feats [N, 8, H, W] (fully written), grad_params [I, 169] and grad_refs [I, 2] (zero-filled
- *   by the callee, then accumulated).
+ * msda_condinst_backward_f32: grad_feats [N, 8, H, W], grad_params [I, 169] and grad_refs [I, 2] (all zero-filled by the
+ *   callee, then accumulated with fp32 reductions: summation order, hence the last bits, vary from run to run).
  * msda_aligned_bilinear_forward/backward_f32: `aligned_bilinear` (ddetrs.py:921-942) on [planes, h, w] -> [planes, f*h, f*w]. */
 int msda_condinst_forward_f32(const float *feats, const float *params, const float *refs, const int32_t *inst_start,
                               int N, int H, int W, int I, int max_inst, int stride, int rel_coord, float *logits,
                               void *stream);
 int msda_condinst_backward_f32(const float *grad_logits, const float *feats, const float *params, const float *refs,
-                               const int32_t *inst_start, int N, int H, int W, int I, int stride, int rel_coord,
-                               float *grad_feats, float *grad_params, float *grad_refs, void *stream);
+                               const int32_t *inst_start, int N, int H, int W, int I, int max_inst, int stride,
+                               int rel_coord, float *grad_feats, float *grad_params, float *grad_refs, void *stream);
 int msda_aligned_bilinear_forward_f32(const float *in, int64_t planes, int h, int w, int factor, float *out, void *stream);
 int msda_aligned_bilinear_backward_f32(const float *grad_out, int64_t planes, int h, int w, int factor, float *grad_in,
                                        void *stream);

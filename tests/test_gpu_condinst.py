@@ -52,7 +52,7 @@ def _holder(ddetrs, rel_coord, mask_out_stride):
 
 
 @pytest.mark.parametrize("factor", [2, 4])
-@pytest.mark.parametrize("shape", [(3, 5, 7), (2, 1, 1), (1, 13, 21)])
+@pytest.mark.parametrize("shape", [(3, 5, 7), (2, 1, 1), (1, 13, 21), (5, 40, 66)])
 def test_aligned_bilinear_matches_reference(ddetrs, factor, shape):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(*shape, generator=g).to(DEV)
@@ -68,7 +68,7 @@ def test_aligned_bilinear_matches_reference(ddetrs, factor, shape):
 
 @pytest.mark.parametrize("rel_coord", [True, False])
 @pytest.mark.parametrize("num_insts,hw,mask_out_stride", [([5, 3], (12, 20), 4), ([0, 7], (9, 11), 4), ([37, 21, 1], (25, 42), 8),
-                                                          ([300], (32, 40), 4)])
+                                                          ([300], (32, 40), 4), ([30, 17], (100, 168), 4), ([3], (7, 9), 2)])
 def test_dynamic_mask_head_matches_reference(ddetrs, rel_coord, num_insts, hw, mask_out_stride):
     g = torch.Generator().manual_seed(2)
     n, (h, w), total = len(num_insts), hw, sum(num_insts)

@@ -43,11 +43,11 @@ SIGNATURES = {
     "msda_sine_pos_embed_forward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, ctypes.c_float, _i, _vp, _vp]),
     "msda_sine_pos_embed_backward_f32": (_i, [_vp, _vp, ctypes.c_int64, _i, _i, ctypes.c_float, _i, _vp, _vp]),
     "msda_condinst_forward_f32": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _vp]),
-    "msda_condinst_backward_f32": (_i, [_vp] * 5 + [_i] * 6 + [_vp] * 4),
+    "msda_condinst_backward_f32": (_i, [_vp] * 5 + [_i] * 7 + [_vp] * 4),
     "msda_aligned_bilinear_forward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, _i, _vp, _vp]),
     "msda_aligned_bilinear_backward_f32": (_i, [_vp, ctypes.c_int64, _i, _i, _i, _vp, _vp]),
 }
-ABI_VERSION = 1
+ABI_VERSION = 2
 (KNOB_SLAB, KNOB_BWD_WIN_ROWS, KNOB_BWD_LIST_CAP, KNOB_FWD_SLAB_CTAS, KNOB_F32_VEC8_FWD, KNOB_F32_VEC8_BWD,
  KNOB_BF16_FINE_ROWS, KNOB_BF16_PACKED_FWD) = range(8)                                                      # include/msda_b200.h
 

@@ -98,7 +98,7 @@ class _DynamicMaskHead(Function):
                                                       n, h, w, i, max_inst, stride, int(rel_coord), logits.data_ptr(),
                                                       _stream()), "msda_condinst_forward_f32")
         ctx.save_for_backward(feats, params, refs, inst_start)
-        ctx.cfg = (stride, int(rel_coord))
+        ctx.cfg = (stride, int(rel_coord), int(max_inst))
         return logits
 
     @staticmethod
@@ -106,14 +106,14 @@ class _DynamicMaskHead(Function):
     def backward(ctx, g):
         lib = _cabi.load()
         feats, params, refs, inst_start = ctx.saved_tensors
-        stride, rel = ctx.cfg
+        stride, rel, max_inst = ctx.cfg
         n, c, h, w = feats.shape
         i = params.shape[0]
         g = g.contiguous().float()
         gf, gp, gr = torch.empty_like(feats), torch.empty_like(params), torch.empty_like(refs)
         with torch.cuda.device(feats.device):
             _cabi.check(lib.msda_condinst_backward_f32(g.data_ptr(), feats.data_ptr(), params.data_ptr(), refs.data_ptr(),
-                                                       inst_start.data_ptr(), n, h, w, i, stride, rel, gf.data_ptr(),
+                                                       inst_start.data_ptr(), n, h, w, i, max_inst, stride, rel, gf.data_ptr(),
                                                        gp.data_ptr(), gr.data_ptr(), _stream()), "msda_condinst_backward_f32")
         return gf, gp, gr, None, None, None, None
 
