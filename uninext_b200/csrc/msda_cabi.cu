@@ -695,9 +695,9 @@ int msda_condinst_forward_f32(const float *feats, const float *params, const flo
         max_inst < 0 || (long long)H * W >= (1ll << 30))
         return MSDA_E_BADARG;
     if (I == 0 || max_inst == 0) return 0;
-    const int HW = H * W, tile = msda::kCiThreads * msda::kCiFwdPpt;
+    const int HW = H * W, tile = msda::kCiFwdThreads * msda::kCiFwdPpt;
     const dim3 grid((unsigned)((HW + tile - 1) / tile), (unsigned)((max_inst + msda::kCiChunk - 1) / msda::kCiChunk), (unsigned)N);
-    msda::condinst_fwd<<<grid, msda::kCiThreads, 0, static_cast<cudaStream_t>(stream)>>>(feats, params, refs, inst_start, HW,
+    msda::condinst_fwd<<<grid, msda::kCiFwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(feats, params, refs, inst_start, HW,
                                                                                           W, stride, rel_coord, logits);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();

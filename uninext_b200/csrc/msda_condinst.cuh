@@ -33,9 +33,11 @@ constexpr int kCiW1 = 0, kCiW2 = kCiCh * kCiIn, kCiW3 = kCiW2 + kCiCh * kCiCh, k
               kCiB3 = kCiB2 + kCiCh;
 constexpr int kCiSums = kCiParams + 2;      // per-instance sums of the backward pass: parameters, then d/d(ref_x, ref_y)
 constexpr int kCiRow = kCiParams + 3;       // shared-memory row: parameters, ref_x, ref_y, pad
-constexpr int kCiThreads = 128;
+constexpr int kCiThreads = 128;             // backward
+constexpr int kCiFwdThreads = 128;          // forward
 constexpr int kCiChunk = 16;                // instances whose parameters are staged in shared memory at a time
-constexpr int kCiFwdPpt = 4, kCiBwdPpt = 2; // pixels per thread
+constexpr int kCiFwdGroups = 1;             // forward: groups of 4 pixels per thread (2: same time at 190 registers)
+constexpr int kCiFwdPpt = 4 * kCiFwdGroups, kCiBwdPpt = 2;      // pixels per thread
 
 // ---- packed fp32 pairs (FFMA2 = `fma.rn.f32x2`): the kernels keep two neighbouring pixels in the halves of a 64-bit register
 // pair.  A pair built from the same scalar twice compiles to FFMA2's scalar-broadcast operand, so a parameter costs one
@@ -98,50 +100,96 @@ __device__ __forceinline__ void ci_forward(WF wf, XF xf, f2 (&h1)[NP][kCiCh], f2
     }
 }
 
+// Forward-only variant: layer 3 folded into layer 2's output loop, so h2 is never held (same summation order).
+template <int NP, class WF, class XF>
+__device__ __forceinline__ void ci_forward_logit(WF wf, XF xf, f2 (&out)[NP]) {
+    f2 h1[NP][kCiCh];
+#pragma unroll
+    for (int o = 0; o < kCiCh; ++o) {
+        f2 a[NP];
+        const f2 bias = wf(kCiB1 + o);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) a[q] = bias;
+#pragma unroll
+        for (int c = 0; c < kCiIn; ++c) {
+            const f2 wt = wf(kCiW1 + o * kCiIn + c);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) a[q] = f2_fma(wt, xf(q, c), a[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) h1[q][o] = f2_relu(a[q]);
+    }
+    const f2 b3 = wf(kCiB3);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) out[q] = b3;
+#pragma unroll
+    for (int o = 0; o < kCiCh; ++o) {
+        f2 a[NP];
+        const f2 bias = wf(kCiB2 + o);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) a[q] = bias;
+#pragma unroll
+        for (int c = 0; c < kCiCh; ++c) {
+            const f2 wt = wf(kCiW2 + o * kCiCh + c);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) a[q] = f2_fma(wt, h1[q][c], a[q]);
+        }
+        const f2 w3 = wf(kCiW3 + o);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) out[q] = f2_fma(w3, f2_relu(a[q]), out[q]);
+    }
+}
+
 __device__ __forceinline__ float ci_loc(int px, int W, int stride, bool want_y) {
     return (float)((want_y ? px / W : px % W) * stride + stride / 2);
 }
 
-// ---- forward: a pair = two neighbouring pixels of one instance; 4 pixels per thread.
+// ---- forward: a pair = two neighbouring pixels of one instance; a thread owns kCiFwdGroups groups of 4 consecutive pixels,
+// group g of thread t at pixel (tile * groups + g) * 4 * blockDim + 4 * t, so every 16-byte access of a warp is contiguous.
 // grid: (pixel tiles, instance chunks, images).  feats [N, 8, H*W]; params [I, 169]; refs [I, 2] (pixels of the input image);
 // inst_start [N + 1] (instances of image b are [inst_start[b], inst_start[b + 1])); logits [I, H*W].
-__global__ void __launch_bounds__(kCiThreads)
+__global__ void __launch_bounds__(kCiFwdThreads)
 condinst_fwd(const float *__restrict__ feats, const float *__restrict__ params, const float *__restrict__ refs,
              const int *__restrict__ inst_start, int HW, int W, int stride, int rel_coord, float *__restrict__ logits)
 {
-    constexpr int PPT = kCiFwdPpt, NP = PPT / 2;
+    constexpr int G = kCiFwdGroups, NP = 2 * G;
     __shared__ __align__(16) float sp[kCiChunk][kCiRow];
     const int b = blockIdx.z;
     const int i0 = inst_start[b] + blockIdx.y * kCiChunk, i1 = min(inst_start[b + 1], i0 + kCiChunk);
     if (i0 >= i1) return;
-    for (int t = threadIdx.x; t < (i1 - i0) * kCiSums; t += kCiThreads) {
+    for (int t = threadIdx.x; t < (i1 - i0) * kCiSums; t += kCiFwdThreads) {
         const int k = t / kCiSums, j = t - k * kCiSums;
         sp[k][j] = j < kCiParams ? params[(size_t)(i0 + k) * kCiParams + j] : refs[(size_t)(i0 + k) * 2 + (j - kCiParams)];
     }
     __syncthreads();
-    const int px0 = (blockIdx.x * kCiThreads + threadIdx.x) * PPT;
-    if (px0 >= HW) return;
-    const bool vec = (HW & 3) == 0;            // then px0 + 4 <= HW and every row of feats / logits is 16-byte aligned
+    int gpx[G];                                 // first pixel of each group
+#pragma unroll
+    for (int g = 0; g < G; ++g) gpx[g] = ((blockIdx.x * G + g) * kCiFwdThreads + threadIdx.x) * 4;
+    if (gpx[0] >= HW) return;
+    const bool vec = (HW & 3) == 0;            // then a live group has 4 pixels and every row of feats / logits is 16-byte aligned
     f2 x[NP][kCiIn], lx[NP], ly[NP];
 #pragma unroll
-    for (int c = 0; c < kCiFeat; ++c) {
-        const float *src = feats + ((size_t)b * kCiFeat + c) * HW + px0;
-        float v[PPT];
-        if (vec) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
+    for (int g = 0; g < G; ++g) {
 #pragma unroll
-            for (int q = 0; q < PPT; ++q) v[q] = px0 + q < HW ? __ldg(src + q) : 0.f;
+        for (int c = 0; c < kCiFeat; ++c) {
+            const float *src = feats + ((size_t)b * kCiFeat + c) * HW + gpx[g];
+            float v[4];
+            if (vec && gpx[g] < HW) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(src));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = gpx[g] + q < HW ? __ldg(src + q) : 0.f;
+            }
+            x[2 * g][2 + c] = f2_make(v[0], v[1]);
+            x[2 * g + 1][2 + c] = f2_make(v[2], v[3]);
         }
 #pragma unroll
-        for (int q = 0; q < NP; ++q) x[q][2 + c] = f2_make(v[2 * q], v[2 * q + 1]);
-    }
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-        const int pa = min(px0 + 2 * q, HW - 1), pb = min(px0 + 2 * q + 1, HW - 1);
-        lx[q] = f2_make(ci_loc(pa, W, stride, false), ci_loc(pb, W, stride, false));
-        ly[q] = f2_make(ci_loc(pa, W, stride, true), ci_loc(pb, W, stride, true));
+        for (int q = 0; q < 2; ++q) {
+            const int pa = min(gpx[g] + 2 * q, HW - 1), pb = min(gpx[g] + 2 * q + 1, HW - 1);
+            lx[2 * g + q] = f2_make(ci_loc(pa, W, stride, false), ci_loc(pb, W, stride, false));
+            ly[2 * g + q] = f2_make(ci_loc(pa, W, stride, true), ci_loc(pb, W, stride, true));
+        }
     }
     const f2 minus1 = f2_bcast(-1.f), zero = f2_bcast(0.f);
     for (int k = 0; k < i1 - i0; ++k) {
@@ -152,16 +200,20 @@ condinst_fwd(const float *__restrict__ feats, const float *__restrict__ params, 
             x[q][0] = rel_coord ? f2_fma(minus1, lx[q], wf(kCiParams)) : zero;          // ref - location, one rounding
             x[q][1] = rel_coord ? f2_fma(minus1, ly[q], wf(kCiParams + 1)) : zero;
         }
-        f2 h1[NP][kCiCh], h2[NP][kCiCh], out[NP];
-        ci_forward<NP>(wf, [&x](int q, int c) { return x[q][c]; }, h1, h2, out);
-        float *dst = logits + (size_t)(i0 + k) * HW + px0;
-        if (vec) {
-            *reinterpret_cast<float4 *>(dst) = make_float4(f2_lo(out[0]), f2_hi(out[0]), f2_lo(out[1]), f2_hi(out[1]));
-        } else {
+        f2 out[NP];
+        ci_forward_logit<NP>(wf, [&x](int q, int c) { return x[q][c]; }, out);
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                if (px0 + 2 * q < HW) dst[2 * q] = f2_lo(out[q]);
-                if (px0 + 2 * q + 1 < HW) dst[2 * q + 1] = f2_hi(out[q]);
+        for (int g = 0; g < G; ++g) {
+            float *dst = logits + (size_t)(i0 + k) * HW + gpx[g];
+            if (vec) {
+                if (gpx[g] < HW)
+                    *reinterpret_cast<float4 *>(dst) = make_float4(f2_lo(out[2 * g]), f2_hi(out[2 * g]), f2_lo(out[2 * g + 1]), f2_hi(out[2 * g + 1]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (gpx[g] + 2 * q < HW) dst[2 * q] = f2_lo(out[2 * g + q]);
+                    if (gpx[g] + 2 * q + 1 < HW) dst[2 * q + 1] = f2_hi(out[2 * g + q]);
+                }
             }
         }
     }
