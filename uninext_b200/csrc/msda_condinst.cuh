@@ -438,21 +438,26 @@ aligned_bilinear2_fwd(const float *__restrict__ in, int h, int w, float *__restr
     const float *src = in + (size_t)blockIdx.x * h * w;
     float *dst = out + (size_t)blockIdx.x * oh * ow;
     const int Y0 = blockIdx.y * kAbRows, rows = min(kAbRows, oh - Y0);
-    for (int t = threadIdx.x; t < rows * owv; t += 256) {
-        const int r = t / owv, Y = Y0 + r, X0 = (t - r * owv) * 4, c = X0 >> 1;
-        const int p = max(Y - 1, 0), y0 = p >> 1;
-        const bool two = (p & 1) != 0;
-        const float *ra = src + (size_t)y0 * w, *rb = src + (size_t)min(y0 + 1, h - 1) * w;
-        float a = __ldg(ra + max(c - 1, 0)), b = __ldg(ra + c), d = __ldg(ra + c + 1);
-        float o0 = X0 == 0 ? b : 0.5f * a + 0.5f * b, o1 = b, o2 = 0.5f * b + 0.5f * d, o3 = d;
-        if (two) {
-            a = __ldg(rb + max(c - 1, 0)); b = __ldg(rb + c); d = __ldg(rb + c + 1);
-            o0 = 0.5f * o0 + 0.5f * (X0 == 0 ? b : 0.5f * a + 0.5f * b);
-            o1 = 0.5f * o1 + 0.5f * b;
-            o2 = 0.5f * o2 + 0.5f * (0.5f * b + 0.5f * d);
-            o3 = 0.5f * o3 + 0.5f * d;
+    // thread -> (column group, first row): one division per thread, none per element
+    const int per = min(owv, 256), rstep = 256 / per, cg0 = threadIdx.x % per, r0 = threadIdx.x / per;
+    if (r0 >= rstep) return;
+    for (int cg = cg0; cg < owv; cg += per) {
+        const int X0 = cg * 4, c = X0 >> 1, cm = max(c - 1, 0);
+        for (int r = r0; r < rows; r += rstep) {
+            const int Y = Y0 + r, p = max(Y - 1, 0), y0 = p >> 1;
+            const bool two = (p & 1) != 0;
+            const float *ra = src + (size_t)y0 * w, *rb = src + (size_t)min(y0 + 1, h - 1) * w;
+            float a = __ldg(ra + cm), b = __ldg(ra + c), d = __ldg(ra + c + 1);
+            float o0 = X0 == 0 ? b : 0.5f * a + 0.5f * b, o1 = b, o2 = 0.5f * b + 0.5f * d, o3 = d;
+            if (two) {
+                a = __ldg(rb + cm); b = __ldg(rb + c); d = __ldg(rb + c + 1);
+                o0 = 0.5f * o0 + 0.5f * (X0 == 0 ? b : 0.5f * a + 0.5f * b);
+                o1 = 0.5f * o1 + 0.5f * b;
+                o2 = 0.5f * o2 + 0.5f * (0.5f * b + 0.5f * d);
+                o3 = 0.5f * o3 + 0.5f * d;
+            }
+            *reinterpret_cast<float4 *>(dst + (size_t)Y * ow + X0) = make_float4(o0, o1, o2, o3);
         }
-        *reinterpret_cast<float4 *>(dst + (size_t)Y * ow + X0) = make_float4(o0, o1, o2, o3);
     }
 }
 
@@ -462,22 +467,27 @@ aligned_bilinear2_bwd(const float *__restrict__ gout, int h, int w, float *__res
     const float *g = gout + (size_t)blockIdx.x * oh * ow;
     float *dst = gin + (size_t)blockIdx.x * h * w;
     const int y0b = blockIdx.y * kAbRows, rows = min(kAbRows, h - y0b);
-    for (int t = threadIdx.x; t < rows * wv; t += 256) {
-        const int r = t / wv, y = y0b + r, x = (t - r * wv) * 2;
+    const int per = min(wv, 256), rstep = 256 / per, cg0 = threadIdx.x % per, r0 = threadIdx.x / per;
+    if (r0 >= rstep) return;
+    for (int cg = cg0; cg < wv; cg += per) {
+        const int x = cg * 2;
         const float wx0 = x == 0 ? 1.f : 0.5f;
         const bool tail = 2 * x + 4 < ow;
-        float s0 = 0.f, s1 = 0.f;
+        for (int r = r0; r < rows; r += rstep) {
+            const int y = y0b + r;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int Y = 2 * y + k;
-            if (Y >= oh) break;
-            const float wy = k == 1 ? 1.f : (k == 0 && y > 0) || k == 2 ? 0.5f : 1.f;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(g + (size_t)Y * ow + 2 * x));
-            const float e = tail ? __ldg(g + (size_t)Y * ow + 2 * x + 4) : 0.f;
-            s0 = fmaf(wy, wx0 * v.x + v.y + 0.5f * v.z, s0);
-            s1 = fmaf(wy, 0.5f * v.z + v.w + 0.5f * e, s1);
+            for (int k = 0; k < 3; ++k) {
+                const int Y = 2 * y + k;
+                if (Y >= oh) break;
+                const float wy = k == 1 ? 1.f : (k == 0 && y > 0) || k == 2 ? 0.5f : 1.f;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(g + (size_t)Y * ow + 2 * x));
+                const float e = tail ? __ldg(g + (size_t)Y * ow + 2 * x + 4) : 0.f;
+                s0 = fmaf(wy, wx0 * v.x + v.y + 0.5f * v.z, s0);
+                s1 = fmaf(wy, 0.5f * v.z + v.w + 0.5f * e, s1);
+            }
+            *reinterpret_cast<float2 *>(dst + (size_t)y * w + x) = make_float2(s0, s1);
         }
-        *reinterpret_cast<float2 *>(dst + (size_t)y * w + x) = make_float2(s0, s1);
     }
 }
 
