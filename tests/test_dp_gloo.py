@@ -40,7 +40,9 @@ def _worker(rank, world, port, q, overlap):
             loss.backward()
             bucket.finish()
         before = dist.get_world_size()
-        q.put((rank, idx, bucket.flat.clone(), before, bucket.n_slices))
+        # by value (a list), not a tensor: a tensor travels as a file descriptor served by THIS process, which may have
+        # exited by the time the parent rebuilds it
+        q.put((rank, idx, bucket.flat.tolist(), before, bucket.n_slices))
     finally:
         dist.destroy_process_group()
 
@@ -54,6 +56,7 @@ def test_two_rank_flat_allreduce_equals_single_process_gradient(overlap):
     for p in procs:
         p.start()
     got = [q.get(timeout=120) for _ in procs]
+    got = [(r, idx, torch.tensor(flat, dtype=torch.float32), w, n) for r, idx, flat, w, n in got]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -43,7 +43,7 @@ def _worker(rank, world, port, q, overlap):
             bucket.finish()
         torch.cuda.synchronize()
         assert not overlap or bucket.n_slices > 4
-        q.put((rank, bucket.flat.cpu()))
+        q.put((rank, bucket.flat.cpu().numpy()))                # by value: a tensor would travel as an fd served by this process
     finally:
         dist.destroy_process_group()
 
@@ -59,7 +59,7 @@ def test_two_gpu_gradients_equal_single_gpu(overlap):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=300) for _ in procs)
+    got = {r: torch.from_numpy(a) for r, a in (q.get(timeout=300) for _ in procs)}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -12,8 +12,9 @@ is the autograd wrapper and the module with the reference's parameter names (``c
 """
 from __future__ import annotations
 
+import functools
 import math
-from typing import List, Sequence
+from typing import List, Sequence, Tuple
 
 import torch
 from torch import nn
@@ -118,6 +119,16 @@ class _DynamicMaskHead(Function):
         return gf, gp, gr, None, None, None, None
 
 
+@functools.lru_cache(maxsize=512)
+def _inst_start(num_insts: Tuple[int, ...], device: torch.device) -> torch.Tensor:
+    """[N + 1] int32 prefix sums on the device; cached because inference repeats the same counts (one tiny H2D copy per
+    distinct tuple instead of per call, and none inside a CUDA-graph capture after the first call)."""
+    starts = [0]
+    for k in num_insts:
+        starts.append(starts[-1] + k)
+    return torch.tensor(starts, dtype=torch.int32, device=device)
+
+
 def dynamic_mask_with_coords(mask_feats: torch.Tensor, reference_points: torch.Tensor, mask_head_params: torch.Tensor,
                              num_insts: Sequence[int], mask_feat_stride: int, rel_coord: bool = True,
                              mask_out_stride: int = 4) -> torch.Tensor:
@@ -143,10 +154,7 @@ def dynamic_mask_with_coords(mask_feats: torch.Tensor, reference_points: torch.T
     if not rel_coord:       # 8-channel first layer: embed into the 10-channel kernel layout with zero coordinate weights
         w1 = params[:, :64].reshape(total, 8, 8)
         params = torch.cat((torch.cat((w1.new_zeros(total, 8, 2), w1), -1).reshape(total, 80), params[:, 64:]), -1)
-    starts = [0]
-    for k in num_insts:
-        starts.append(starts[-1] + int(k))
-    inst_start = torch.tensor(starts, dtype=torch.int32).to(mask_feats.device, non_blocking=True)
+    inst_start = _inst_start(tuple(int(k) for k in num_insts), mask_feats.device)
     logits = _DynamicMaskHead.apply(mask_feats, params, reference_points.reshape(total, 2), inst_start,
                                     int(max(num_insts)), int(mask_feat_stride), bool(rel_coord))
     logits = aligned_bilinear(logits, mask_feat_stride // mask_out_stride)
