@@ -35,6 +35,9 @@ feats = torch.randn(2, 8, 12, 20, device="cuda", requires_grad=True)
 refs = (torch.rand(1, 21, 2, device="cuda") * 100).requires_grad_(True)
 params = (torch.randn(1, 21, 169, device="cuda") * 0.3).requires_grad_(True)
 dynamic_mask_with_coords(feats, refs, params, [17, 4], 8).square().mean().backward()
+feats = torch.randn(2, 8, 9, 11, device="cuda", requires_grad=True)        # odd sizes: scalar tails, generic aligned_bilinear
+dynamic_mask_with_coords(feats, refs, params, [0, 21], 8).square().mean().backward()
+dynamic_mask_with_coords(feats, refs, params, [20, 1], 8, True, 2).square().mean().backward()
 # W-stationary tcgen05 GEMM with mask + ReLU
 from uninext_b200.functions.fused import tcgen05_linear_ex
 c = tcgen05_linear_ex(torch.randn(300, 256, device="cuda"), torch.randn(256, 256, device="cuda"), torch.randn(256, device="cuda"),
