@@ -47,3 +47,13 @@ for ql,(H,W) in enumerate(shapes):
         v = r.reshape(-1); v = v[v>=0]
         tot_tile += len(v); uniq_tile += len(np.unique(v))
     print(f"query level {ql} ({H}x{W}): unique/total row-adds per warp step (4 neighbours x 1 tap x 4 corners) {uniq_step/tot_step:.3f}; per 8x8-patch tile (64 pairs x 16 taps x 4 corners) {uniq_tile/tot_tile:.3f}")
+
+# the 16 corner rows of ONE (query, head, level): could a lane group combine its own taps in registers before issuing?
+tot = uniq = 0
+for _ in range(2000):
+    q = rng.integers(0, S); m = rng.integers(0, 8)
+    r = rows_of(np.array([q]), m)[0]                  # [L, P, corner]
+    for l in range(4):
+        v = r[l].reshape(-1); v = v[v >= 0]
+        tot += len(v); uniq += len(np.unique(v))
+print(f"one (query, head, level), 4 taps x 4 corners: unique/total {uniq / tot:.3f}")
