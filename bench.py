@@ -393,11 +393,14 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
     g = torch.Generator(device=device).manual_seed(77 + rank)
     src = torch.randn(cfg.batch, cfg.S, 256, device=device, generator=g)
     pos = torch.randn(cfg.batch, cfg.S, 256, device=device, generator=g)
+    # the reference always hands MSDeformAttn its padding mask (all-False for unpadded frames), so
+    # value_proj is always followed by the masked_fill -- here fused into the GEMM's epilogue when TF32 products are allowed
+    pad = torch.zeros(cfg.batch, cfg.S, dtype=torch.bool, device=device)
 
     def train_step(amp):
         bucket.zero_()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            out = model(src, pos, shapes, ss, lsi)
+            out = model(src, pos, shapes, ss, lsi, pad)
         out.float().square().mean().backward()
         bucket.finish()
 
@@ -424,7 +427,7 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
 
     res = {"steps": steps, "frames_per_gpu": cfg.batch, "grad_allreduce_bytes": bucket.nbytes,
            "what": "6 enc + 6 dec deformable transformer layers fwd+bwd + one flat gradient all-reduce; synthetic "
-                   "features, backbone/heads/losses excluded. fp32 = strict fp32 GEMMs (cfg2's dtype); tf32 = "
+                   "features and an all-False padding mask, backbone/heads/losses excluded. fp32 = strict fp32 GEMMs (cfg2's dtype); tf32 = "
                    "torch.backends.cuda.matmul.allow_tf32 (the default of the reference's PyTorch 1.10 stack); "
                    "amp_bf16 = autocast, MSDeformAttn still fp32 as in the reference (custom_fwd cast)"}
     res["fp32"] = measure(False)
@@ -445,7 +448,7 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
 
         def captured():
             bucket.zero_()
-            model(src, pos, shapes, ss, lsi).float().square().mean().backward()
+            model(src, pos, shapes, ss, lsi, pad).float().square().mean().backward()
         graph = GraphedStep(captured, warmup=3, device=device)
 
         def graphed_step(_amp):

@@ -204,6 +204,9 @@ int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t 
 int msda_linear_tf32_ex(const float *A, const float *W, const float *bias, const uint8_t *row_mask, int64_t M, int N, int K,
                         int relu, float *C, void *stream);
 int msda_linear_tf32_ws_ok(int N, int K);
+/* Diagnostic: phase timeline of the last 2-CTA W-stationary GEMM launched with MSDA_GEMM_WS_DBG=1 (160 CTAs x 24 slots of
+ * SM-clock stamps; layout in msda_gemm_sm100.cu).  Copies min(n_words, 3840) words to `out` (host). */
+int msda_debug_gemm_timeline(unsigned long long *out, int n_words);
 
 #ifdef __cplusplus
 }

@@ -250,6 +250,15 @@ def test_module_tcgen05_gemm_with_fused_mask():
         got = mod(x, ref, x, ss, lsi, mask)
         got.square().mean().backward()
         assert torch.isfinite(x.grad).all()
+        # gemm="auto": cuBLAS, except value_proj WITH a padding mask under allow_tf32 (fused mask epilogue beats GEMM + masked_fill)
+        mod.gemm = "auto"
+        auto_fp32 = mod(src, ref, src, ss, lsi, mask)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        auto_tf32 = mod(src, ref, src, ss, lsi, mask)
+        auto_nomask = mod(src, ref, src, ss, lsi, None)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
     assert _rel(got, want) < 1e-2
+    assert torch.equal(auto_fp32, want)                                 # strict fp32: the cuBLAS path, bit for bit
+    assert _rel(auto_tf32, want) < 1e-2 and torch.isfinite(auto_nomask).all()
+    assert (auto_tf32[1, -200:] - auto_fp32[1, -200:]).abs().max() < 1e-2

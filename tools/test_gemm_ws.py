@@ -19,7 +19,7 @@ def ws(a, w, b, mask=None, relu=False):
 
 torch.manual_seed(0)
 ok = True
-TIMING_ONLY = os.environ.get("MSDA_GEMM_WS_EPI", "")[:1] in ("n", "l")          # experiment modes write no output
+TIMING_ONLY = os.environ.get("MSDA_GEMM_WS_EPI", "")[:1] in ("n", "l", "x")          # experiment modes write no output
 for (m, n, k, use_mask, relu, use_bias) in [(128, 256, 256, 0, 0, 1), (64, 64, 32, 0, 0, 1), (1, 128, 64, 0, 0, 1), (300, 256, 256, 1, 0, 1),
                                             (1000, 192, 128, 1, 1, 1), (44646, 256, 256, 1, 0, 1), (44646, 256, 256, 0, 1, 0),
                                             (513, 64, 256, 0, 0, 1), (77, 128, 96, 1, 1, 0), (20000, 256, 32, 0, 0, 1)]:
@@ -47,7 +47,12 @@ for (m, n, k) in [(44646, 256, 256), (65280, 256, 256), (25500, 256, 256), (4464
     c = torch.empty(m, n, device="cuda")
     def stream_kernel():
         os.environ["MSDA_GEMM_WS"] = "0"
-    fns = (("tcgen05-ws", lambda: ws(a, w, b)), ("cublas-tf32", lambda: torch.addmm(b, a, w.t(), out=c)))
+    mask = (torch.rand(m, device="cuda") < 0.1)
+    mask8 = mask.to(torch.uint8)
+    # value_proj as the reference runs it (ops/modules/ms_deform_attn.py:95-97): Linear, then masked_fill of the padded rows
+    fns = (("tcgen05-ws", lambda: ws(a, w, b)), ("cublas-tf32", lambda: torch.addmm(b, a, w.t(), out=c)),
+           ("tcgen05-ws+mask", lambda: ws(a, w, b, mask8)),
+           ("cublas+masked_fill", lambda: torch.addmm(b, a, w.t(), out=c).masked_fill_(mask[:, None], 0.0)))
     for name, fn in fns:
         for _ in range(5): fn()
         torch.cuda.synchronize()
@@ -63,4 +68,4 @@ for (m, n, k) in [(44646, 256, 256), (65280, 256, 256), (25500, 256, 256), (4464
         e0.record()
         for _ in range(20): fn()
         e1.record(); torch.cuda.synchronize()
-        print(f"{name:12s} M={m} N={n} K={k}: cold-L2 median {ts[10]*1e3:.1f} us, back-to-back {e0.elapsed_time(e1)/20*1e3:.1f} us", flush=True)
+        print(f"{name:18s} M={m} N={n} K={k}: cold-L2 median {ts[10]*1e3:.1f} us, back-to-back {e0.elapsed_time(e1)/20*1e3:.1f} us", flush=True)

@@ -30,6 +30,7 @@ constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one s
 constexpr int UMMA_K = 8;                   // tf32: 32 bytes per instruction
 constexpr int kThreads = 192;
 constexpr int kMaxN = 512;
+constexpr int kEpiWarpsWS2 = 8, kThreadsWS2 = 64 + 32 * kEpiWarpsWS2;   // 2-CTA W-stationary kernel: producer, MMA, 8 epilogue warps
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -270,6 +271,8 @@ struct ParamsWS {
     const float *bias;
     const unsigned char *row_mask;      // [M] bytes, non-zero = zero the whole output row; may be null
     float *C;
+    long long rows_per_pair;            // 2-CTA kernel: contiguous rows per CTA pair (multiple of 32)
+    int dbg;                            // 2-CTA kernel: 1 = record the phase timeline
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -464,6 +467,232 @@ linear_tf32_ws_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols) : "memory");
 }
 
+// =====================================================================================================================
+// W-STATIONARY, 2-CTA MMA (cta_group::2).  Same residency as above -- CTA r of the pair keeps rows [r N/2, (r+1) N/2) of W
+// in shared memory -- but the pair now works on a 256-row tile with ONE tcgen05.mma.cta_group::2 (M = 256, N = N) per k-step,
+// issued by the leader CTA: each CTA supplies its own 128 rows of A and its half of W, and receives the accumulator of
+// its 128 rows x all N columns in its own tensor memory.  Per output row that halves the two big shared-memory streams of
+// the 1-CTA version (the MMA's operand reads -- a tf32 MMA pulls 8 KB per 69-cycle instruction, the whole port -- and the
+// TMA writes: no CTA receives rows it does not own), which is what bounded it (shared memory: 512 KB per 128 rows there,
+// 640 KB per 256 rows here).
+//   barriers: the A stage of BOTH CTAs completes on the LEADER's full barrier (the peer's TMA signals it through the
+//   shared::cluster address with the CTA-rank bit cleared); tcgen05.commit multicasts "stage free" and "accumulator full" to
+//   both CTAs; the epilogue warps of both CTAs arrive on the leader's "accumulator empty" barrier (count 8).
+__device__ __forceinline__ unsigned leader_addr(const void *p) { return smem_u32(p) & 0xFEFFFFFFu; }   // same offset in the pair's even CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, unsigned bar_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((unsigned)accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// Diagnostic timeline (MSDA_GEMM_WS_DBG=1): per CTA, SM-clock stamps of the phases below, read back with
+// msda_debug_gemm_timeline().  Slot 0: %globaltimer at entry (ns); 1: entry; 2: set-up done; 3: first stage landed;
+// 4 + 2 i / 5 + 2 i: accumulator of tile i complete / stored (epilogue warp 2); 20: producer done; 21: MMA issue done; 22: exit.
+constexpr int kTlSlots = 24;
+__device__ unsigned long long g_ws2_timeline[160][kTlSlots];
+__device__ __forceinline__ void tl_stamp(int dbg, int slot) {
+    if (dbg && blockIdx.x < 160) g_ws2_timeline[blockIdx.x][slot] = (unsigned long long)clock64();
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsWS2, 1)
+linear_tf32_ws2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ CUtensorMap map_c, const ParamsWS p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2], w_bar[8];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.dbg && threadIdx.x == 0 && blockIdx.x < 160) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        g_ws2_timeline[blockIdx.x][0] = gt;
+        tl_stamp(1, 1);
+    }
+    const int N = p.N, NH = N / 2, KB = p.K / BLOCK_K;
+    const unsigned a_bytes = BLOCK_M * BLOCK_K * 4;                     // this CTA's 128 rows of one k-block
+    const unsigned wk_bytes = (unsigned)NH * BLOCK_K * 4;               // one k-block of this CTA's half of W
+    unsigned char *w_res = smem;
+    unsigned char *stages = smem + (size_t)KB * wk_bytes;
+    const unsigned rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    // Rows are dealt out in equal contiguous ranges (multiples of 32 = one store box), not in whole 256-row tiles: with
+    // 175 tiles on 74 pairs a third of the machine would run a third round alone.  A pair walks its range in 256-row
+    // tiles; the last one may be short: CTA r then owns rows [ts + r h, ts + (r + 1) h) with h < 128 (the loads and the MMA
+    // still cover 128 rows per CTA -- extra rows are real rows of A whose results are simply not stored).
+    const long long range0 = (long long)(blockIdx.x / 2) * p.rows_per_pair;
+    const long long range1 = range0 + p.rows_per_pair < p.M ? range0 + p.rows_per_pair : p.M;
+    const int ntiles = range1 > range0 ? (int)((range1 - range0 + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) : 0;
+    auto tile_rows = [&](int i, long long &row0) -> int {               // -> h, and this CTA's first row
+        const long long ts = range0 + (long long)i * 2 * BLOCK_M, rem = range1 - ts;
+        const int h = rem >= 2 * BLOCK_M ? BLOCK_M : (int)((rem + 63) / 64) * 32;
+        row0 = ts + (long long)rank * h;
+        return h;
+    };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 2 * kEpiWarpsWS2); }
+        for (int i = 0; i < 8; ++i) mbar_init(&w_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((unsigned)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    // (allocating AFTER the cluster barrier, overlapped with the first loads, measured slower: the pair's allocation takes
+    // ~1.5 us and then sits on the leader's critical path, which must know the PEER's tensor memory is ready too)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    if (threadIdx.x == 0) tl_stamp(p.dbg, 2);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own half of W once, then own 128 rows of every tile; completion on the leader =====
+        if (lane == 0) {
+            // W arrives k-block by k-block, each with its own barrier, interleaved with the first tile's A stages, so the
+            // first MMA waits for 16 + 16 KB, not for the whole 128 KB of W.
+            int kbw = 0;
+            auto load_w = [&]() {
+                if (leader) mbar_expect_tx(&w_bar[kbw], 2u * wk_bytes);
+                tma_load_2d_2sm(w_res + (size_t)kbw * wk_bytes, &map_w, kbw * BLOCK_K, (int)rank * NH, leader_addr(&w_bar[kbw]));
+                ++kbw;
+            };
+            unsigned s = 0, ph = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                long long row0;
+                tile_rows(i, row0);
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (i == 0 && kb < p.stages && kbw < KB) load_w();
+                    if (i == 0 && kb == p.stages) while (kbw < KB) load_w();         // before the first wait that can block
+                    mbar_wait(&empty_bar[s], ph ^ 1);                    // the pair's MMA has drained this stage (commit reaches both CTAs)
+                    if (leader) mbar_expect_tx(&full_bar[s], 2u * a_bytes);
+                    tma_load_2d_2sm(stages + (size_t)s * a_bytes, &map_a, kb * BLOCK_K, (int)row0, leader_addr(&full_bar[s]));
+                    if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
+                }
+                while (i == 0 && kbw < KB) load_w();                                 // K / 32 <= stages
+            }
+            tl_stamp(p.dbg, 20);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's elected lane drives both CTAs' tensor cores =====
+        if (leader) {
+            unsigned tt = 0;
+            const uint32_t idesc = umma_idesc_tf32(2 * BLOCK_M, N);
+            const uint64_t a_desc0 = umma_desc(stages, 0), w_desc0 = umma_desc(w_res, 0);
+            const uint32_t a_step = a_bytes >> 4, w_step = wk_bytes >> 4, k_step = (UMMA_K * 4) >> 4;
+            unsigned s = 0, ph = 0;
+            for (; tt < (unsigned)ntiles; ++tt) {
+                const unsigned buf = tt & 1, use = tt >> 1;
+                mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * (uint32_t)N;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (tt == 0) mbar_wait(&w_bar[kb], 0);               // both halves of this k-block of W are resident
+                    mbar_wait(&full_bar[s], ph);
+                    if (tt == 0 && kb == 0 && lane == 0) tl_stamp(p.dbg, 3);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint64_t ad = a_desc0 + (uint64_t)(s * a_step), wd = w_desc0 + (uint64_t)((unsigned)kb * w_step);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma2_tf32(acc, ad + (uint64_t)(k * k_step), wd + (uint64_t)(k * k_step), idesc, (kb | k) != 0);
+                        umma2_commit_mc(&empty_bar[s], (uint16_t)3);
+                        if (kb == KB - 1) umma2_commit_mc(&tmem_full_bar[buf], (uint16_t)3);
+                    }
+                    __syncwarp();
+                    if (++s == (unsigned)p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+            if (lane == 0) tl_stamp(p.dbg, 21);
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows x N columns.  A warp may only touch the tensor-memory lanes of its quadrant
+        // (warp % 4), so the 8 epilogue warps pair up per quadrant and split the columns.  Per 32-column chunk:
+        // tcgen05.ld (thread = row, 32 consecutive columns) -> fused tail in registers -> the row goes into the warp's
+        // 32 x 128-byte staging tile in TMA's SWIZZLE_128B order (16-byte chunk j of row r at chunk j ^ (r % 8)) -> one TMA
+        // store of the 32 x 32 box (rows past M are clipped by the tensor map).  No shared-memory read-back by the warp and
+        // no per-thread global stores: the 1-CTA kernel's transposing epilogue was its slowest phase (5.5 us per tile).
+        const int ew = warp - 2;
+        const int lane_base = (warp & 3) * 32;
+        const int col_lo = (ew >> 2) * NH;                               // this warp's NH columns
+        float *xp = reinterpret_cast<float *>(stages + (size_t)p.stages * a_bytes + (size_t)ew * (32 * 32 * 4));
+        for (unsigned tt = 0; tt < (unsigned)ntiles; ++tt) {
+            const unsigned buf = tt & 1, use = tt >> 1;
+            mbar_wait(&tmem_full_bar[buf], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 2 && lane == 0 && tt < 8) tl_stamp(p.dbg, 4 + 2 * (int)tt);
+            long long row0;
+            const int h = tile_rows((int)tt, row0);
+            const long long row_base = row0 + lane_base;
+            const long long r = row_base + lane;
+            const bool dead = p.row_mask != nullptr && r < p.M && p.row_mask[r] != 0;
+            if (p.direct_epilogue != 2 && lane_base < h)                // a short tile leaves the upper quadrants without rows
+            for (int c0 = col_lo; c0 < col_lo + NH; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + buf * (uint32_t)N + (uint32_t)c0, v);
+                if (p.direct_epilogue == 3) {                            // timing experiment: tensor-memory loads only
+                    if (v[0] == 123.456f && row_base < 0) p.C[0] = v[1];
+                    continue;
+                }
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + 4 * j));     // warp-uniform address
+                        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (p.relu) v[i] = fmaxf(v[i], 0.f);
+                    if (dead) v[i] = 0.f;
+                }
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // previous box has left the staging tile
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(xp + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                        // generic-proxy writes -> visible to the TMA
+                __syncwarp();
+                if (lane == 0 && row_base < p.M) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                 ::"l"(&map_c), "r"(c0), "r"((int)row_base), "r"(smem_u32(xp)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (warp == 2 && lane == 0 && tt < 8) tl_stamp(p.dbg, 5 + 2 * (int)tt);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(&tmem_empty_bar[buf])) : "memory");
+        }
+    }
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tile has been read; the writes complete with the grid
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x == 0) tl_stamp(p.dbg, 22);
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)p.tmem_cols) : "memory");
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -533,6 +762,8 @@ int launch_ws(const float *A, const float *W, const float *bias, const unsigned 
     }
     ParamsWS p;
     p.multicast = mc;
+    p.rows_per_pair = 0;
+    p.dbg = 0;
     p.direct_epilogue = direct >= 2 ? direct : (direct == 1 && ((reinterpret_cast<uintptr_t>(C) & 31u) == 0) && (N % 16 == 0)) ? 1 : 0;
     p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
     const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
@@ -555,6 +786,51 @@ int launch_ws(const float *A, const float *W, const float *bias, const unsigned 
     return (int)cudaGetLastError();
 }
 
+int launch_ws2(const float *A, const float *W, const float *bias, const unsigned char *row_mask, long long M, int N, int K,
+               int relu, float *C, cudaStream_t stream) {
+    CUtensorMap map_a, map_w, map_c;
+    if (!make_map(&map_a, A, M, K, BLOCK_M) || !make_map(&map_w, W, N, K, N / 2) || !make_map(&map_c, C, M, N, 32))
+        return MSDA_E_NODEVICE;
+    static int epi = -1;                     // MSDA_GEMM_WS_EPI=none: timing experiment without the epilogue's work
+    if (epi < 0) {                           // none / ldonly: timing experiments, no valid output
+        const char *e = getenv("MSDA_GEMM_WS_EPI");
+        epi = (e && e[0] == 'n') ? 2 : (e && e[0] == 'l') ? 3 : 0;
+    }
+    ParamsWS p;
+    p.multicast = 0; p.direct_epilogue = epi;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("MSDA_GEMM_WS_DBG"); dbg = (e && e[0] == '1') ? 1 : 0; }
+    p.dbg = dbg;
+    p.M = M; p.N = N; p.K = K; p.relu = relu; p.bias = bias; p.row_mask = row_mask; p.C = C;
+    const size_t w_half = (size_t)(N / 2) * K * 4, a_stage = BLOCK_M * BLOCK_K * 4;
+    constexpr size_t kDynMax = 232448 - 1024;
+    constexpr size_t kXpose = (size_t)kEpiWarpsWS2 * 32 * 32 * 4;              // one swizzled 32 x 32 staging tile per epilogue warp
+    int stages = (int)((kDynMax - 1024 - kXpose - w_half) / a_stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return MSDA_E_BADARG;
+    p.stages = stages;
+    p.tmem_cols = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 2 * N <= 256 ? 256 : 512;    // 2 accumulators of N columns
+    const size_t smem = w_half + (size_t)stages * a_stage + kXpose + 1024;
+    static std::atomic<int> cache[64];
+    const int sms = sms_for_device(reinterpret_cast<const void *>(linear_tf32_ws2_kernel), (int)kDynMax, cache);
+    if (sms < 0) return MSDA_E_NODEVICE;
+    const long long tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const long long max_clusters = sms / 2;
+    const long long pairs = tiles < max_clusters ? tiles : max_clusters;
+    p.rows_per_pair = (((M + pairs - 1) / pairs) + 31) / 32 * 32;
+    const unsigned grid = 2u * (unsigned)pairs;
+    linear_tf32_ws2_kernel<<<grid, kThreadsWS2, smem, stream>>>(map_a, map_w, map_c, p);
+    g_msda_gemm_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+// which W-stationary kernel: the 2-CTA MMA version unless MSDA_GEMM_WS2=0 (the 1-CTA kernel with multicast A, kept for A/B runs)
+bool use_ws2() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MSDA_GEMM_WS2"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 }  // namespace gemm
 
 extern "C" int msda_linear_tf32_ex(const float *A, const float *W, const float *bias, const uint8_t *row_mask, int64_t M, int N,
@@ -564,10 +840,18 @@ extern "C" int msda_linear_tf32_ex(const float *A, const float *W, const float *
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15u) return MSDA_E_BADARG;
     if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return MSDA_E_BADARG;
     if (!ws_ok(N, K)) return MSDA_E_BADARG;
+    if (use_ws2() && K <= 8 * BLOCK_K)        // the 2-CTA kernel keeps one barrier per k-block of W (8)
+        return launch_ws2(A, W, bias, row_mask, M, N, K, relu ? 1 : 0, C, static_cast<cudaStream_t>(stream));
     return launch_ws(A, W, bias, row_mask, M, N, K, relu ? 1 : 0, C, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int msda_linear_tf32_ws_ok(int N, int K) { return gemm::ws_ok(N, K) ? 1 : 0; }
+
+extern "C" int msda_debug_gemm_timeline(unsigned long long *out, int n_words) {
+    if (!out || n_words <= 0) return MSDA_E_BADARG;
+    const size_t want = sizeof(unsigned long long) * (size_t)n_words, have = sizeof(unsigned long long) * 160 * gemm::kTlSlots;
+    return (int)cudaMemcpyFromSymbol(out, gemm::g_ws2_timeline, want < have ? want : have);
+}
 
 extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t M, int N, int K, float *C,
                                 void *stream) {
@@ -578,7 +862,9 @@ extern "C" int msda_linear_tf32(const float *A, const float *W, const float *bia
     {
         static int ws = -1;
         if (ws < 0) { const char *e = getenv("MSDA_GEMM_WS"); ws = (e && e[0] == '0') ? 0 : 1; }
-        if (ws && ws_ok(N, K)) return launch_ws(A, W, bias, nullptr, M, N, K, 0, C, static_cast<cudaStream_t>(stream));
+        if (ws && ws_ok(N, K))
+            return use_ws2() && K <= 8 * BLOCK_K ? launch_ws2(A, W, bias, nullptr, M, N, K, 0, C, static_cast<cudaStream_t>(stream))
+                             : launch_ws(A, W, bias, nullptr, M, N, K, 0, C, static_cast<cudaStream_t>(stream));
     }
     if (N > 256 && (N % 64)) return MSDA_E_BADARG;      // MMA N tiles are multiples of 16, W halves whole swizzle atoms
     const int w_box_rows = N / 2;                       // each CTA of the pair loads (and multicasts) half of W

@@ -80,6 +80,7 @@ def tcgen05_linear(x2: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor
 # cuBLAS TF32 is still ahead on these shapes, so auto resolves to cuBLAS unless MSDA_GEMM_AUTO=tcgen05 is set.
 import os as _os
 _AUTO_TCGEN05 = _os.environ.get("MSDA_GEMM_AUTO", "cublas") == "tcgen05"
+_AUTO_MASKED_TCGEN05 = _os.environ.get("MSDA_GEMM_AUTO_MASKED", "tcgen05") == "tcgen05"     # value_proj + padding mask
 
 
 def resolve_gemm(gemm: str) -> str:
@@ -105,7 +106,8 @@ def tcgen05_linear_ex(x2, weight, bias, row_mask=None, relu=False):
     out = torch.empty((m, n), dtype=torch.float32, device=x2.device)
     mask8 = None
     if row_mask is not None:
-        mask8 = row_mask.reshape(-1).to(torch.uint8).contiguous()          # bool -> bytes (a view-compatible copy, M bytes)
+        mask8 = row_mask.reshape(-1).contiguous()
+        mask8 = mask8.view(torch.uint8) if mask8.dtype == torch.bool else mask8.to(torch.uint8)       # bool is one byte: no copy
     with torch.cuda.device(x2.device):
         _cabi.check(_cabi.load().msda_linear_tf32_ex(x2.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                                      mask8.data_ptr() if mask8 is not None else None, m, n, k, int(relu),
@@ -124,7 +126,10 @@ class _LinearColsum(Function):
     def forward(ctx, x, weight, bias, relu, gemm, row_mask):
         x2 = x.reshape(-1, x.shape[-1])
         mask = row_mask.reshape(-1) if row_mask is not None else None
-        if resolve_gemm(gemm) == "tcgen05" and tcgen05_ws_ok(x2, weight):
+        # "auto" with a row mask: the fused kernel replaces GEMM + masked_fill (21.7 us against 19.2 + 14 us at 44 646 x 256 x 256,
+        # profiles/r02ah_gemm_ws2.txt), so it is taken whenever TF32 products are allowed; without a mask cuBLAS stays ahead.
+        fused_mask = gemm == "auto" and mask is not None and torch.backends.cuda.matmul.allow_tf32 and _AUTO_MASKED_TCGEN05
+        if (resolve_gemm(gemm) == "tcgen05" or fused_mask) and tcgen05_ws_ok(x2, weight):
             y = tcgen05_linear_ex(x2, weight, bias, mask, relu)          # bias, padding-mask zeroing and ReLU in the epilogue
         elif relu:                                           # bias + ReLU in the cuBLASLt epilogue
             y = torch._addmm_activation(bias, x2, weight.t(), use_gelu=False)

@@ -143,8 +143,9 @@ class DeformableStack(nn.Module):
         self.register_buffer("reference_boxes", boxes)
         self.n_levels = n_levels
 
-    def forward(self, src, pos, spatial_shapes_list, spatial_shapes, level_start_index):
-        """src, pos: [N, S, C] flattened multi-scale features / position encodings.  Returns decoder output [N, Q, C]."""
+    def forward(self, src, pos, spatial_shapes_list, spatial_shapes, level_start_index, padding_mask=None):
+        """src, pos: [N, S, C] flattened multi-scale features / position encodings; padding_mask [N, S] bool (the reference
+        always passes its `mask_flatten`, deformable_transformer.py:190-205).  Returns decoder output [N, Q, C]."""
         n = src.shape[0]
         valid = torch.ones(n, self.n_levels, 2, device=src.device)
         ref = encoder_reference_points(spatial_shapes_list, valid, src.device)
@@ -153,16 +154,16 @@ class DeformableStack(nn.Module):
                                for i, (h, w) in enumerate(spatial_shapes_list)], 1)
         memory = src
         for layer in self.encoder:
-            memory = layer(memory, pos, ref, spatial_shapes, level_start_index, None)
+            memory = layer(memory, pos, ref, spatial_shapes, level_start_index, padding_mask)
         qpos, tgt = self.query_embed.weight.chunk(2, dim=-1)
         qpos, tgt = qpos[None].expand(n, -1, -1), tgt[None].expand(n, -1, -1)
         boxes = self.reference_boxes[None].expand(n, -1, -1)                              # [N, Q, 4] (cx, cy, w, h)
         ref_dec = boxes[:, :, None] * torch.cat((valid, valid), -1)[:, None]             # deformable_transformer.py:457-459
         out = tgt
         if use_batched_value_proj():                                 # memory is loop-invariant: one [256 -> 6 x 256] GEMM
-            values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, None)
+            values = batched_value_proj([layer.cross_attn for layer in self.decoder], memory, padding_mask)
         else:
             values = [None] * len(self.decoder)
         for layer, val in zip(self.decoder, values):
-            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, None, projected_value=val)
+            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, padding_mask, projected_value=val)
         return out
