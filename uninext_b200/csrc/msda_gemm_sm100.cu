@@ -664,17 +664,20 @@ linear_tf32_ws2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     if (p.relu) v[i] = fmaxf(v[i], 0.f);
                     if (dead) v[i] = 0.f;
                 }
+                // (borrowing the idle A stages as extra staging tiles in the last tile, so that no box waits for the previous
+                // store to drain, was measured: no change -- the tail is the memory system draining, not this wait)
+                float *tile = xp;
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // previous box has left the staging tile
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4 *>(xp + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                    *reinterpret_cast<float4 *>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                        // generic-proxy writes -> visible to the TMA
                 __syncwarp();
                 if (lane == 0 && row_base < p.M) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
-                                 ::"l"(&map_c), "r"(c0), "r"((int)row_base), "r"(smem_u32(xp)) : "memory");
+                                 ::"l"(&map_c), "r"(c0), "r"((int)row_base), "r"(smem_u32(tile)) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
