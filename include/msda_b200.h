@@ -200,7 +200,9 @@ int msda_linear_tf32(const float *A, const float *W, const float *bias, int64_t 
 /* W-stationary variant with a fused tail, for K <= 256 and N <= 256 (N % 64 == 0; msda_linear_tf32_ws_ok tells):
  *   C = A . W^T + bias;  rows with row_mask[m] != 0 are written as zeros (the `masked_fill(input_padding_mask)` that follows
  *   value_proj, ops/modules/ms_deform_attn.py:96-97);  relu != 0 applies max(., 0) (FFN linear1).  bias / row_mask may be NULL.
- *   msda_linear_tf32 itself routes eligible shapes to this kernel. */
+ *   msda_linear_tf32 itself routes eligible shapes to this kernel.  Two implementations: for K <= 256 a 2-CTA MMA kernel
+ *   (tcgen05.mma.cta_group::2, M = 256 per CTA pair, TMA-store epilogue), otherwise / with MSDA_GEMM_WS2=0 the 1-CTA kernel
+ *   with multicast A.  A, W, C (and bias) must be 16-byte aligned. */
 int msda_linear_tf32_ex(const float *A, const float *W, const float *bias, const uint8_t *row_mask, int64_t M, int N, int K,
                         int relu, float *C, void *stream);
 int msda_linear_tf32_ws_ok(int N, int K);
