@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps K --warmup W      # the reference's CPU path (torch port) on host cores
+    python bench.py --impl reference --steps K --warmup W      # the reference's own CPU path on the host cores
 
 One *step* = one pass of the hot path over one batch of the workload (default cfg2 = BASELINE.json configs[1]:
 COCO-shape 1333x800, R50 4-level features, 300 queries, 8 heads x 32, 4 levels x 4 points, batch 2, fp32): the
@@ -19,7 +19,8 @@ Reported (one JSON line, rank 0):
   e2e        -- same metric with HOST (pinned) inputs and results: H2D of value/loc/attn/grad_out and D2H of
                 out/grad_value/grad_loc/grad_attn inside the timed region.
   roofline   -- dominant kernel (encoder-shaped backward: memset + msda_bwd_tiled) against the measured HBM peak.
-  cpu_baseline -- torch port of the reference's ms_deform_attn_core_pytorch CPU path on this box's host cores.
+  cpu_baseline -- the reference's ms_deform_attn_core_pytorch CPU path (its own file, staged in oracle/_ref; the
+                  torch port pinned to it when no staged copy exists) on this box's host cores.
 """
 from __future__ import annotations
 
@@ -294,11 +295,7 @@ def run_b200(args):
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.dtype == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": cfg.name, "levels": cfg.shapes, "S": cfg.S, "frames_per_gpu": cfg.batch,
-                       "heads": cfg.heads, "head_dim": cfg.head_dim, "points": cfg.points,
-                       "dec_queries": cfg.dec_queries, "calls_per_step": f"{N_ENC} enc + {N_DEC} dec, fwd+bwd",
-                       "samples_per_step_per_gpu": smp_step, "parallelism": f"dp{world} (frames sharded, no exchange)",
-                       "l2_policy": "12 distinct input sets per step (~1 GB) > 126 MB L2"},
+            "config": step_config(cfg, world),
             "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
             "gsamples_per_s": {"enc_fwd": round(cfg.samples("enc") / kern["enc_fwd_ms"] / 1e6, 2),
                                "enc_bwd": round(cfg.samples("enc") / kern["enc_bwd_ms"] / 1e6, 2),
@@ -585,9 +582,32 @@ def run_e2e(MSDA, calls, op_args, world, smp_step, steps, device, barrier):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU legs: the reference's CPU path (torch port of ms_deform_attn_core_pytorch; oracle/ is test infrastructure and
+# CPU legs: the reference's CPU path (ms_deform_attn_core_pytorch, reference file or port; oracle/ is test infrastructure and
 # is imported here ONLY as the measured baseline, never by the product path).
 # ------------------------------------------------------------------------------------------------------------------
+def cpu_path():
+    """-> (fn, kind, description): the reference's own ``ms_deform_attn_core_pytorch`` loaded from the staged copy of the
+    reference file (oracle/_ref, put there by build() in the build container; kind "reference"), else the torch port
+    that tests/golden pins to it (kind "port")."""
+    from oracle import refpy
+    fn = refpy.core_pytorch()
+    if fn is not None:
+        return fn, "reference", ("the reference's own ms_deform_attn_core_pytorch (ops/functions/ms_deform_attn_func.py:43-63, "
+                                 "unmodified file staged in oracle/_ref; grid_sample per level) fwd + autograd bwd")
+    from oracle.msda_oracle import core_pytorch_port
+    return core_pytorch_port, "port", ("torch port of the reference's ms_deform_attn_core_pytorch (no staged copy of the "
+                                       "reference file on this box; the port is pinned to it by tests/golden) fwd + autograd bwd")
+
+
+def step_config(cfg, world):
+    """The `config` object of the JSON line -- identical for the product arm and the reference arm."""
+    return {"workload": cfg.name, "levels": cfg.shapes, "S": cfg.S, "frames_per_gpu": cfg.batch,
+            "heads": cfg.heads, "head_dim": cfg.head_dim, "points": cfg.points,
+            "dec_queries": cfg.dec_queries, "calls_per_step": f"{N_ENC} enc + {N_DEC} dec, fwd+bwd",
+            "samples_per_step_per_gpu": samples_per_step(cfg), "parallelism": f"dp{world} (frames sharded, no exchange)",
+            "l2_policy": "12 distinct input sets per step (~1 GB) > 126 MB L2"}
+
+
 def cpu_call(port, c):
     v = c["value"].clone().requires_grad_(True)
     lo = c["sampling_locations"].clone().requires_grad_(True)
@@ -663,12 +683,11 @@ def cpu_time_sample(port, cfg, budget_s, max_reps):
 
 
 def cpu_baseline(cfg, budget_s):
-    from oracle.msda_oracle import core_pytorch_port
-    threads, cores = cpu_pick_threads(core_pytorch_port, cfg)
-    smp, dt, reps, what = cpu_time_sample(core_pytorch_port, cfg, budget_s, 10)
-    return {"value": round(smp / dt / 1e9, 5), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
-            "impl": "torch port of ms_deform_attn_core_pytorch (grid_sample per level) fwd + autograd bwd; thread count "
-                    "= fastest of {all, 64, 32, 16, 8}",
+    fn, kind, desc = cpu_path()
+    threads, cores = cpu_pick_threads(fn, cfg)
+    smp, dt, reps, what = cpu_time_sample(fn, cfg, budget_s, 10)
+    return {"value": round(smp / dt / 1e9, 5), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind,
+            "impl": desc + "; thread count = fastest of {all, 64, 32, 16, 8}",
             "sample": f"{reps} x ({what})", "seconds_per_sample": round(dt, 3)}
 
 
@@ -678,16 +697,16 @@ def run_reference(args):
     world, rank, _ = dist_env()
     if rank != 0:
         return
-    from oracle.msda_oracle import core_pytorch_port
+    cpu_fn, kind, desc = cpu_path()
     cfg = CONFIGS[args.config]
-    threads, cores = cpu_pick_threads(core_pytorch_port, cfg)
+    threads, cores = cpu_pick_threads(cpu_fn, cfg)
     total = max(1, args.steps + args.warmup)
     per_step_budget = min(12.0, 150.0 / total)
     frames, enc_q = cfg.batch, None
     calls, smp = cpu_sample_calls(cfg, frames, enc_q)
     t0 = time.perf_counter()
     for c in calls:
-        cpu_call(core_pytorch_port, c)
+        cpu_call(cpu_fn, c)
     probe = time.perf_counter() - t0
     if probe > per_step_budget and frames > 1:
         frames, probe = 1, probe / cfg.batch
@@ -697,11 +716,11 @@ def run_reference(args):
         calls, smp = cpu_sample_calls(cfg, frames, enc_q)
     for _ in range(max(0, args.warmup - 1)):
         for c in calls:
-            cpu_call(core_pytorch_port, c)
+            cpu_call(cpu_fn, c)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for c in calls:
-            cpu_call(core_pytorch_port, c)
+            cpu_call(cpu_fn, c)
     dt = (time.perf_counter() - t0) / args.steps
     val = round(smp / dt / 1e9, 5)
     sample = (f"per step: 1 encoder-shaped ({'all' if enc_q is None else enc_q} of {cfg.S} queries) + 1 decoder-shaped "
@@ -710,12 +729,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg.name, "levels": cfg.shapes, "S": cfg.S, "frames_per_gpu": cfg.batch,
-                   "heads": cfg.heads, "head_dim": cfg.head_dim, "points": cfg.points, "dec_queries": cfg.dec_queries},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port", "sample": sample,
-                         "impl": "torch port of the reference's ms_deform_attn_core_pytorch (the reference file cannot "
-                                 "travel to the GPU box; the port is pinned to it by tests/golden); thread count = "
-                                 "fastest of {all, 64, 32, 16, 8}"},
+        "config": step_config(cfg, max(1, args.gpus)),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "host_cores": cores, "kind": kind, "sample": sample,
+                         "impl": desc + "; thread count = fastest of {all, 64, 32, 16, 8}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 

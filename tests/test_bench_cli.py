@@ -28,8 +28,42 @@ def test_reference_arm_prints_contract_line():
         assert key in line, key
     assert line["steps"] == 2 and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == line["value"] and cb["cores"] >= 1 and "sample" in cb
+    sys.path.insert(0, ROOT)
+    from oracle import refpy
+    assert cb["kind"] == ("reference" if refpy.available() else "port")
+    assert cb["value"] == line["value"] and cb["cores"] >= 1 and "sample" in cb
     assert line["config"]["workload"].startswith("cfg1")
+    # same `config` object as the product arm prints (the driver compares the two lines)
+    import bench
+    from uninext_b200.workloads import CONFIGS
+    assert line["config"] == json.loads(json.dumps(bench.step_config(CONFIGS["cfg1"], 1)))
+
+
+def test_reference_file_and_port_agree():
+    """The reference's own ms_deform_attn_core_pytorch (staged file) and the port bench.py falls back to are the same
+    function: identical outputs and autograd gradients on a seeded case."""
+    sys.path.insert(0, ROOT)
+    from oracle import refpy
+    from oracle.msda_oracle import core_pytorch_port
+    if os.path.isdir("/root/reference"):
+        assert refpy.stage()
+    ref = refpy.core_pytorch()
+    if ref is None:
+        pytest.skip("no staged copy of the reference file on this box")
+    from uninext_b200.workloads import CONFIGS, make_inputs
+    c = make_inputs(CONFIGS["cfg1"], "dec", "cpu", seed=5, wild_fraction=0.1)
+    res = []
+    for fn in (ref, core_pytorch_port):
+        v = c["value"].clone().requires_grad_(True)
+        lo = c["sampling_locations"].clone().requires_grad_(True)
+        at = c["attention_weights"].clone().requires_grad_(True)
+        out = fn(v, c["spatial_shapes"], lo, at)
+        out.backward(c["grad_output"])
+        res.append((out.detach(), v.grad, lo.grad, at.grad))
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    assert "MultiScaleDeformableAttention" not in sys.modules or \
+        getattr(sys.modules["MultiScaleDeformableAttention"], "__file__", None) is not None   # the stand-in is gone
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
