@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-frames", action="store_true", help="skip the whole-model frames/s measurement")
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the reference's own CUDA kernels")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config (cfg3/4/5 bf16) kernel table")
+    ap.add_argument("--no-reference-stack", action="store_true",
+                    help="skip timing the reference's own layer classes on its own CUDA kernels (frames.reference_stack)")
     ap.add_argument("--frames-steps", type=int, default=5)
     ap.add_argument("--cpu-budget-s", type=float, default=25.0, help="target CPU seconds for the cpu_baseline sample")
     return ap.parse_args()
@@ -275,7 +277,8 @@ def run_b200(args):
 
     frames = None
     if not args.no_frames:
-        frames = run_frames(cfg, world, rank, device, args.frames_steps, barrier, lib)
+        frames = run_frames(cfg, world, rank, device, args.frames_steps, barrier, lib,
+                            reference_stack=not args.no_reference_stack)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,7 +376,7 @@ def other_configs_leg(MSDA, device, peak):
     return res
 
 
-def run_frames(cfg, world, rank, device, steps, barrier, lib):
+def run_frames(cfg, world, rank, device, steps, barrier, lib, reference_stack=True):
     """Whole-model frames/s: one training step of the 6-encoder + 6-decoder-layer deformable transformer (fwd + bwd,
     fp32, d_model 256, d_ffn 2048) on synthetic multi-scale features of the workload's shape; frames sharded over ranks,
     ONE flat NCCL all-reduce of all parameter gradients per step.  Backbone, heads, matcher and losses are excluded."""
@@ -459,9 +462,110 @@ def run_frames(cfg, world, rank, device, steps, barrier, lib):
         res["tf32_cuda_graph"] = {"unavailable": repr(exc)[:200]}
     bucket.overlap = overlap_was
     torch.backends.cuda.matmul.allow_tf32 = old
+    if rank == 0 and world == 1 and reference_stack:
+        res["reference_stack"] = reference_stack_leg(cfg, device, steps, lib, (src, pos, shapes, ss, lsi, pad), res)
     res["grad_exchange"] = (f"overlapped: {bucket.n_slices} slices all-reduced from grad hooks during backward (eager legs); "
                             "one flat all-reduce after the replay (cuda-graph leg)") if world > 1 else "single GPU: none"
     return res
+
+
+def reference_kernels_module(refcuda):
+    """What the reference's pybind module is to ms_deform_attn_func.py:18, backed by the reference's own kernels
+    (oracle/refcuda.py -> oracle/_ref/libmsda_refcuda.so)."""
+    class _ReferenceKernels:
+        @staticmethod
+        def ms_deform_attn_forward(value, shapes, lsi, loc, attn, im2col_step):
+            return refcuda.forward(value, shapes, lsi, loc, attn)
+
+        @staticmethod
+        def ms_deform_attn_backward(value, shapes, lsi, loc, attn, grad_output, im2col_step):
+            return list(refcuda.backward(value, shapes, lsi, loc, attn, grad_output.contiguous()))
+    return _ReferenceKernels
+
+
+def build_reference_stack(cfg, tr_mod, num_layers=6, d_ffn=2048):
+    """run_frames' model with the REFERENCE's layer classes (module `tr_mod` = the staged deformable_transformer.py) in
+    place of this repo's: same embeddings, reference points, wiring and loss; weights from the same seed."""
+    from uninext_b200.modules.deformable_layers import DeformableStack
+    torch.manual_seed(1234)
+    model = DeformableStack(num_layers=num_layers, num_queries=cfg.dec_queries, d_ffn=d_ffn)
+    kw = dict(d_model=256, d_ffn=d_ffn, dropout=0.0, activation="relu", n_levels=len(cfg.shapes), n_heads=cfg.heads,
+              n_points=cfg.points)
+    model.encoder = torch.nn.ModuleList(tr_mod.DeformableTransformerEncoderLayer(**kw) for _ in range(num_layers))
+    model.decoder = torch.nn.ModuleList(tr_mod.DeformableTransformerDecoderLayer(**kw) for _ in range(num_layers))
+    return model
+
+
+def reference_stack_leg(cfg, device, steps, lib, inputs, ours):
+    """The anchor for frames/s: the SAME step (6 + 6 layers fwd + bwd, same synthetic features, same loss) run by the
+    REFERENCE's GPU stack -- its own Python classes (``DeformableTransformerEncoderLayer`` / ``DecoderLayer`` /
+    ``MSDeformAttn`` / ``MSDeformAttnFunction`` of deformable_transformer.py and ops/, unmodified files staged in tests/_ref)
+    on its own CUDA kernels (ms_deform_im2col_cuda.cuh compiled unmodified into oracle/_ref/libmsda_refcuda.so).  None of
+    this repo's kernels is on that path (checked with the library's launch counter).  Baseline leg only, outside every
+    timed region of this repo's numbers, like `reference_cuda`."""
+    try:
+        from oracle import refcuda
+        from tests import stage_reference
+        if not stage_reference.staged():
+            return {"unavailable": "tests/_ref not staged (needs /root/reference at build time)"}
+        if not refcuda.available():
+            return {"unavailable": "oracle/_ref/libmsda_refcuda.so not built (needs /root/reference at build time)"}
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            func_mod, _attn_mod, tr_mod, _dino_mod = stage_reference.import_reference()
+
+        src, pos, shapes, ss, lsi, pad = inputs
+        model = build_reference_stack(cfg, tr_mod).to(device)
+        was = func_mod.MSDA
+        func_mod.MSDA = reference_kernels_module(refcuda)
+        try:
+            def step():
+                model.zero_grad(set_to_none=True)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    model(src, pos, shapes, ss, lsi, pad).float().square().mean().backward()
+
+            def measure():
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                l0 = lib.msda_launch_count()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(steps):
+                    step()
+                t1.record()
+                torch.cuda.synchronize()
+                ms = t0.elapsed_time(t1) / steps
+                return {"frames_per_s": round(cfg.batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 3),
+                        "msda_b200_launches_per_step": int((lib.msda_launch_count() - l0) / steps)}
+
+            res = {"what": "the reference's own layer classes (deformable_transformer.py:321-416, ops/modules, ops/functions; "
+                           "unmodified files, tests/_ref) on the reference's own CUDA kernels (oracle/_ref), eager PyTorch as "
+                           "the reference runs them; same step, features and loss as the legs above; single GPU"}
+            old = torch.backends.cuda.matmul.allow_tf32
+            try:
+                torch.backends.cuda.matmul.allow_tf32 = False
+                res["fp32"] = measure()
+                torch.backends.cuda.matmul.allow_tf32 = True
+                res["tf32"] = measure()
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = old
+        finally:
+            func_mod.MSDA = was
+        ratio = lambda a, b: round(a / b, 2) if a and b else None
+        res["speedup"] = {
+            "fp32": ratio(ours.get("fp32", {}).get("frames_per_s"), res["fp32"]["frames_per_s"]),
+            "tf32": ratio(ours.get("tf32", {}).get("frames_per_s"), res["tf32"]["frames_per_s"]),
+            "tf32_cuda_graph_vs_reference_tf32": ratio(ours.get("tf32_cuda_graph", {}).get("frames_per_s"),
+                                                       res["tf32"]["frames_per_s"])}
+        del model
+        torch.cuda.empty_cache()
+        return res
+    except Exception as exc:                        # a baseline leg must never take the bench line down
+        return {"unavailable": repr(exc)[:300]}
+
 
 
 def _measure_with(step_fn, steps, barrier, lib, world, device, cfg):

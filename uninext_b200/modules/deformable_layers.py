@@ -165,5 +165,8 @@ class DeformableStack(nn.Module):
         else:
             values = [None] * len(self.decoder)
         for layer, val in zip(self.decoder, values):
-            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, padding_mask, projected_value=val)
+            # `projected_value` only when there is one: any layer with the reference's forward signature (e.g. the
+            # reference's own class, bench.py's reference_stack leg) can stand in `self.decoder`
+            extra = {} if val is None else {"projected_value": val}
+            out = layer(out, qpos, ref_dec, memory, spatial_shapes, level_start_index, padding_mask, **extra)
         return out
