@@ -360,6 +360,30 @@ def test_errors_match_reference_convention():
     assert MSDA.ms_deform_attn_forward(v3, a[1], a[2], lo3, at3, 64).shape[0] == 3
 
 
+def test_empty_and_inconsistent_inputs():
+    """Zero queries: the reference hands back its zero-filled outputs (at::zeros, cu:54,121-123) after an empty launch
+    that only printf's an error (cuh:948-952); same results here, without the failed launch.  Inconsistent shapes, which
+    are out-of-bounds accesses in the reference, raise."""
+    cfg = CONFIGS["cfg1"]
+    inp = make_inputs(cfg, "dec", DEV, seed=8)
+    v, ss, lsi = inp["value"], inp["spatial_shapes"], inp["level_start_index"]
+    lo0, at0 = inp["sampling_locations"][:, :0].contiguous(), inp["attention_weights"][:, :0].contiguous()
+    for dt in (torch.float32, torch.bfloat16):
+        out = MSDA.ms_deform_attn_forward(v.to(dt), ss, lsi, lo0, at0, 64)
+        assert out.shape == (v.shape[0], 0, v.shape[2] * v.shape[3]) and out.dtype == dt
+        gv, gl, ga = MSDA.ms_deform_attn_backward(v.to(dt), ss, lsi, lo0, at0, out, 64)
+        assert gv.shape == v.shape and gv.dtype == dt and not gv.any() and gl.shape == lo0.shape and ga.shape == at0.shape
+    fn_out = MSDeformAttnFunction.apply(v.clone().requires_grad_(True), ss, lsi, lo0, at0, 64)
+    fn_out.sum().backward()                                          # autograd through the empty call
+    with pytest.raises(RuntimeError, match="attn_weight must be"):
+        MSDA.ms_deform_attn_forward(v, ss, lsi, inp["sampling_locations"], inp["attention_weights"][:, :-1].contiguous(), 64)
+    with pytest.raises(RuntimeError, match="level_start_index must be"):
+        MSDA.ms_deform_attn_forward(v, ss, lsi[:-1].contiguous(), inp["sampling_locations"], inp["attention_weights"], 64)
+    with pytest.raises(RuntimeError, match="grad_output must be"):
+        MSDA.ms_deform_attn_backward(v, ss, lsi, inp["sampling_locations"], inp["attention_weights"],
+                                     inp["grad_output"][:, :-1].contiguous(), 64)
+
+
 def test_runs_on_the_callers_stream():
     cfg = CONFIGS["cfg1"]
     inp = make_inputs(cfg, "enc", DEV, seed=6)

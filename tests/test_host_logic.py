@@ -28,6 +28,26 @@ def test_dropin_exports_reference_names_and_refuses_cpu():
         M.ms_deform_attn_forward(v, *_cpu_args()[1:], 64)
 
 
+def test_shape_cross_checks_reject_inconsistent_tensors():
+    """The reference reads sizes from each tensor without cross-checking (cu:40-48); the drop-in refuses instead."""
+    from uninext_b200.dropin import MultiScaleDeformableAttention as M
+    v, ss, lsi, loc, at = _cpu_args()
+    M._check_shapes(v, ss, lsi, loc, at)                                    # consistent: passes
+    M._check_shapes(v, ss, lsi, loc, at, torch.zeros(1, 1, 2))
+    bad = [
+        (v[0], ss, lsi, loc, at, None, "value must be"),
+        (v, ss.view(-1), lsi, loc, at, None, "spatial_shapes must be"),
+        (v, ss, torch.tensor([0, 4]), loc, at, None, "level_start_index must be"),
+        (v, ss, lsi, torch.zeros(1, 1, 2, 1, 1, 2), at, None, "sampling_loc must be"),       # heads differ from value
+        (v, ss, lsi, torch.zeros(1, 1, 1, 2, 1, 2), at, None, "sampling_loc must be"),       # levels differ
+        (v, ss, lsi, loc, torch.zeros(1, 1, 1, 1, 3), None, "attn_weight must be"),
+        (v, ss, lsi, loc, at, torch.zeros(1, 2, 2), "grad_output must be"),
+    ]
+    for *args, go, msg in bad:
+        with pytest.raises(RuntimeError, match=msg):
+            M._check_shapes(*args, go)
+
+
 def test_function_signature_matches_reference():
     from uninext_b200.functions import MSDeformAttnFunction
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):

@@ -52,6 +52,29 @@ def _same_dtype(value, *named):
             raise RuntimeError(f"{name} must be {want} when value is {value.dtype}, got {t.dtype}")
 
 
+def _check_shapes(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output=None):
+    """The reference reads every size from the tensors and never cross-checks them (cu:40-48): inconsistent shapes are
+    out-of-bounds reads / reds there.  Here they are a RuntimeError before anything is launched."""
+    if value.dim() != 4:
+        raise RuntimeError(f"value must be [N, S, M, D], got {tuple(value.shape)}")
+    n, s, m, d = value.shape
+    if spatial_shapes.dim() != 2 or spatial_shapes.size(1) != 2:
+        raise RuntimeError(f"spatial_shapes must be [L, 2], got {tuple(spatial_shapes.shape)}")
+    l = spatial_shapes.size(0)
+    if level_start_index.dim() != 1 or level_start_index.size(0) != l:
+        raise RuntimeError(f"level_start_index must be [L] = [{l}], got {tuple(level_start_index.shape)}")
+    if sampling_loc.dim() != 6 or sampling_loc.size(0) != n or sampling_loc.size(2) != m or sampling_loc.size(3) != l \
+            or sampling_loc.size(5) != 2:
+        raise RuntimeError(f"sampling_loc must be [N, Lq, M, L, P, 2] = [{n}, Lq, {m}, {l}, P, 2], got "
+                           f"{tuple(sampling_loc.shape)}")
+    if tuple(attn_weight.shape) != tuple(sampling_loc.shape[:5]):
+        raise RuntimeError(f"attn_weight must be [N, Lq, M, L, P] = {tuple(sampling_loc.shape[:5])}, got "
+                           f"{tuple(attn_weight.shape)}")
+    if grad_output is not None and (grad_output.size(0) != n or grad_output.numel() != n * sampling_loc.size(1) * m * d):
+        raise RuntimeError(f"grad_output must be [N, Lq, M*D] = [{n}, {sampling_loc.size(1)}, {m * d}], got "
+                           f"{tuple(grad_output.shape)}")
+
+
 def _level_tensor(t, name):
     if t.dtype != torch.int64:
         raise RuntimeError(f"{name} must be an int64 tensor")                      # cu:67-68 data<int64_t>()
@@ -64,7 +87,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
              ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)], value, im2col_step)
     _same_dtype(value, ("sampling_loc", sampling_loc), ("attn_weight", attn_weight))
     _level_tensor(spatial_shapes, "spatial_shapes"); _level_tensor(level_start_index, "level_start_index")
+    _check_shapes(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     n, s, m, d, l, lq, p = dims = _dims(value, spatial_shapes, sampling_loc)
+    if min(dims) == 0:        # nothing to sample: the reference returns its at::zeros output (cu:54) after a failed empty launch
+        return torch.zeros((n, lq, m * d), dtype=value.dtype, device=value.device)
     lib = _cabi.load()
     with torch.cuda.device(value.device):
         out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
@@ -88,7 +114,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if grad_output.dtype != value.dtype:
         raise RuntimeError(f"grad_output dtype {grad_output.dtype} != value dtype {value.dtype}")
     _level_tensor(spatial_shapes, "spatial_shapes"); _level_tensor(level_start_index, "level_start_index")
+    _check_shapes(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output)
     dims = _dims(value, spatial_shapes, sampling_loc)
+    if min(dims) == 0:        # empty problem: the reference's three zeros_like results (cu:121-123)
+        gv_dtype = torch.float32 if (value.dtype == torch.bfloat16 and grad_value_dtype == torch.float32) else value.dtype
+        return [torch.zeros(value.shape, dtype=gv_dtype, device=value.device), torch.zeros_like(sampling_loc),
+                torch.zeros_like(attn_weight)]
     lib = _cabi.load()
     with torch.cuda.device(value.device):
         grad_loc = torch.empty_like(sampling_loc)
