@@ -10,8 +10,9 @@ Two restatements live here:
   the bit-level restatement of the reference CUDA kernels' arithmetic
   (``ops/src/cuda/ms_deform_im2col_cuda.cuh:33-159,237-403``). numpy arrays in, numpy arrays out.
 * ``core_pytorch_port``: a torch restatement of the reference's *CPU path*, ``ms_deform_attn_core_pytorch``
-  (``ops/functions/ms_deform_attn_func.py:43-63``): one ``grid_sample`` per level, weighted sum. This is what the
-  ``--impl reference`` arm of bench.py times (the reference file itself cannot travel to the GPU box).
+  (``ops/functions/ms_deform_attn_func.py:43-63``): one ``grid_sample`` per level, weighted sum. The
+  ``--impl reference`` arm of bench.py times the reference file itself when ``build()`` staged it (``oracle/refpy.py``
+  -> ``oracle/_ref/``) and falls back to this port otherwise.
 
 Parity pin: both are checked against golden vectors generated from the reference's own
 ``ms_deform_attn_core_pytorch`` (tests/golden/make_golden.py -> tests/golden/*.npz).
