@@ -74,7 +74,11 @@ uint64_t msda_launch_count(void);
  *                                   grad_value directly in bf16 (packed 8-byte reds); the others in fp32.  0 = all fp32.
  *                                   (changes results within the 1e-2 bf16 tolerance, see DESIGN.md.)
  *   MSDA_KNOB_BF16_PACKED_FWD       bf16 forward (D = 32 / 64, large launches): blend the 4 corners of a tap in packed bf16 and
- *                                   accumulate taps in fp32 (~3 extra bf16 roundings per tap; also changes results slightly). */
+ *                                   accumulate taps in fp32 (~3 extra bf16 roundings per tap; also changes results slightly).
+ *   MSDA_KNOB_ZERO_FILL             how msda_backward_* zero-fills grad_value (results identical): 0 = cudaMemsetAsync,
+ *                                   1 = msda_zero_fill kernel (16-byte stores, one wave), 2 = the same kernel launched as the
+ *                                   programmatic-dependent-launch primary of the tiled backward kernel, whose prologue then
+ *                                   overlaps the fill (not while the stream is being captured into a CUDA graph). */
 #define MSDA_KNOB_SLAB          0
 #define MSDA_KNOB_BWD_WIN_ROWS  1
 #define MSDA_KNOB_BWD_LIST_CAP  2
@@ -83,7 +87,9 @@ uint64_t msda_launch_count(void);
 #define MSDA_KNOB_F32_VEC8_BWD  5   /* fp32 tiled backward: same lane shape; 0 / 1                                     */
 #define MSDA_KNOB_BF16_FINE_ROWS 6  /* bf16 backward: levels with H*W >= this accumulate grad_value in bf16; 0 = off */
 #define MSDA_KNOB_BF16_PACKED_FWD 7 /* bf16 forward: corners of a tap blended in packed bf16 (HFMA2); 0 / 1            */
-#define MSDA_KNOB_COUNT         8
+#define MSDA_KNOB_ZERO_FILL     8   /* grad_value zero-fill of the backward: 0 cudaMemsetAsync, 1 own kernel, 2 own kernel
+                                       as the PDL primary of the tiled backward kernel (prologue overlaps the fill)   */
+#define MSDA_KNOB_COUNT         9
 #define MSDA_KNOB_QUERY         (-1000000)
 int msda_set_knob(int knob, int value);
 

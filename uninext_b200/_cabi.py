@@ -50,7 +50,7 @@ SIGNATURES = {
 }
 ABI_VERSION = 2
 (KNOB_SLAB, KNOB_BWD_WIN_ROWS, KNOB_BWD_LIST_CAP, KNOB_FWD_SLAB_CTAS, KNOB_F32_VEC8_FWD, KNOB_F32_VEC8_BWD,
- KNOB_BF16_FINE_ROWS, KNOB_BF16_PACKED_FWD) = range(8)                                                      # include/msda_b200.h
+ KNOB_BF16_FINE_ROWS, KNOB_BF16_PACKED_FWD, KNOB_ZERO_FILL) = range(9)                                                      # include/msda_b200.h
 
 _lib = None
 

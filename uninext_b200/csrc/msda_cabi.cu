@@ -68,10 +68,35 @@ struct Knobs {
         v[MSDA_KNOB_F32_VEC8_BWD].store(env_int("MSDA_F32_VEC8_BWD", 0));
         v[MSDA_KNOB_BF16_FINE_ROWS].store(env_int("MSDA_BF16_FINE_ROWS", 0));
         v[MSDA_KNOB_BF16_PACKED_FWD].store(env_int("MSDA_BF16_PACKED_FWD", 0));
+        v[MSDA_KNOB_ZERO_FILL].store(env_int("MSDA_ZERO_FILL", 0));
     }
 };
 Knobs &knobs() { static Knobs k; return k; }
 int knob(int i) { return knobs().v[i].load(std::memory_order_relaxed); }
+
+// Set by msda_backward_* when the zero-fill just issued on the stream may be the PDL primary of the next launch; consumed
+// (and cleared) by launch_bwd, cleared by msda_backward_* on every other route.
+thread_local bool t_pdl_next = false;
+
+// Zero-fill of grad_value before the backward kernels (MSDA_KNOB_ZERO_FILL).  *pdl is set when the fill went out as a
+// kernel that the NEXT launch on `st` may take as its programmatic-dependent-launch primary.  The fill kernel stands in
+// for a memset and is not counted by msda_launch_count().
+cudaError_t zero_fill(void *p, size_t bytes, cudaStream_t st, bool *pdl = nullptr) {
+    if (pdl) *pdl = false;
+    const int mode = knob(MSDA_KNOB_ZERO_FILL);
+    if (mode <= 0 || bytes < (1u << 16) || !aligned16(p) || (bytes & 15u)) return cudaMemsetAsync(p, 0, bytes, st);
+    const unsigned long long n16 = bytes >> 4;
+    unsigned long long blocks = (n16 + 255) / 256;
+    const unsigned long long wave = (unsigned long long)num_sms() * 8;       // 8 x 256 threads = every thread slot of an SM
+    if (blocks > wave) blocks = wave;
+    msda::msda_zero_fill<<<(unsigned)blocks, 256, 0, st>>>(static_cast<uint4 *>(p), n16);
+    const cudaError_t err = cudaGetLastError();
+    if (pdl && mode >= 2 && err == cudaSuccess) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        *pdl = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    }
+    return err;
+}
 
 // ---- routing ------------------------------------------------------------------------------------------------
 // Fast path: D in {16,32,64} (fp32) / {32,64} (bf16), L <= kMaxLevels, L*P <= 32.  LP_MAX is the compile-time tap
@@ -201,6 +226,24 @@ cudaError_t launch_bwd(const T *grad_out, const T *value, const int64_t *shapes,
     const unsigned iter_pairs = msda::kTiledWarps * (split ? 1 : GPW);
     const unsigned tiles_ub = (npairs + iter_pairs - 1) / iter_pairs;
     const int grid = (int)(tiles_ub < (unsigned)slots ? tiles_ub : (unsigned)slots);
+    const bool pdl = t_pdl_next;
+    t_pdl_next = false;
+    if (pdl) {       // the preceding launch on `st` is msda_zero_fill(grad_value): let this kernel's prologue overlap it
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(msda::kTiledThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq,
+                                                 d.P, npairs, allow_patches(), gv, gl, ga, (__nv_bfloat16 *)nullptr, 0);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     kern<<<grid, msda::kTiledThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, d.N, d.S, d.M, d.L, d.Lq, d.P,
                                                npairs, allow_patches(), gv, gl, ga, nullptr, 0);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -480,11 +523,16 @@ int msda_backward_f32(const float *grad_out, const float *value, const int64_t *
     MSDA_CHECK_PTRS(al, grad_out, value, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight);
     if (!spatial_shapes || !level_start_index) return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * S * M * D, st);
+    bool pdl = false;
+    cudaError_t err = zero_fill(grad_value, sizeof(float) * (size_t)N * S * M * D, st, &pdl);
     if (err != cudaSuccess) return (int)err;
-    if (al && use_fast(4, d))
-        return (int)bwd_fast<float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
-                                    grad_value, grad_sampling_loc, grad_attn_weight, st);
+    if (al && use_fast(4, d)) {
+        t_pdl_next = pdl;
+        err = bwd_fast<float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
+                              grad_value, grad_sampling_loc, grad_attn_weight, st);
+        t_pdl_next = false;
+        return (int)err;
+    }
     return (int)bwd_generic<float, float, float>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
                                                  attn_weight, d, grad_value, grad_sampling_loc, grad_attn_weight, st);
 }
@@ -499,7 +547,7 @@ int msda_backward_f64(const double *grad_out, const double *value, const int64_t
         !grad_sampling_loc || !grad_attn_weight)
         return MSDA_E_BADARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t err = cudaMemsetAsync(grad_value, 0, sizeof(double) * (size_t)N * S * M * D, st);
+    cudaError_t err = zero_fill(grad_value, sizeof(double) * (size_t)N * S * M * D, st);
     if (err != cudaSuccess) return (int)err;
     return (int)bwd_generic<double, double, double>(grad_out, value, spatial_shapes, level_start_index, sampling_loc,
                                                     attn_weight, d, grad_value, grad_sampling_loc, grad_attn_weight, st);
@@ -523,7 +571,7 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
         // mixed accumulation: bf16 result zero-filled (fine levels add into it), fp32 scratch zero-filled for the coarse
         // levels only, one rounding pass over the coarse rows at the end -- no full-size fp32 round trip
         __nv_bfloat16 *gv16 = reinterpret_cast<__nv_bfloat16 *>(grad_value);
-        cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(uint16_t) * nval, st);
+        cudaError_t e = zero_fill(grad_value, sizeof(uint16_t) * nval, st);
         if (e != cudaSuccess) return (int)e;
         const dim3 hgrid((unsigned)(num_sms() * 2 / (N < 1 ? 1 : N) + 1), (unsigned)N);
         msda::msda_coarse_rows<false><<<hgrid, 256, 0, st>>>(grad_value_f32, gv16, spatial_shapes, level_start_index, L, S,
@@ -537,12 +585,15 @@ int msda_backward_bf16(const uint16_t *grad_out, const uint16_t *value, const in
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return (int)cudaGetLastError();
     }
-    cudaError_t err = cudaMemsetAsync(grad_value_f32, 0, sizeof(float) * nval, st);
+    bool pdl = false;
+    cudaError_t err = zero_fill(grad_value_f32, sizeof(float) * nval, st, &pdl);
     if (err != cudaSuccess) return (int)err;
-    if (al && use_fast(2, d))
+    if (al && use_fast(2, d)) {
+        t_pdl_next = pdl;
         err = bwd_fast<__nv_bfloat16>(go, v, spatial_shapes, level_start_index, sampling_loc, attn_weight, d,
                                       grad_value_f32, grad_sampling_loc, grad_attn_weight, st);
-    else
+        t_pdl_next = false;
+    } else
         err = bwd_generic<__nv_bfloat16, float, float>(go, v, spatial_shapes, level_start_index, sampling_loc,
                                                        attn_weight, d, grad_value_f32, grad_sampling_loc,
                                                        grad_attn_weight, st);

@@ -444,6 +444,7 @@ msda_bwd_tiled(const T *__restrict__ grad_out, const T *__restrict__ value,
         }
         __syncwarp();
     }
+    pdl_wait_primary();      // grad_value's zero-fill (msda_zero_fill as PDL primary) is complete and visible from here on
 
     for (unsigned tile = blockIdx.x; tile < wm.ntiles; tile += gridDim.x) {
         const TileCtx tc = decode_tile(wm, tile, L, M);
