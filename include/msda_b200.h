@@ -78,7 +78,8 @@ uint64_t msda_launch_count(void);
  *   MSDA_KNOB_ZERO_FILL             how msda_backward_* zero-fills grad_value (results identical): 0 = cudaMemsetAsync,
  *                                   1 = msda_zero_fill kernel (16-byte stores, one wave), 2 = the same kernel launched as the
  *                                   programmatic-dependent-launch primary of the tiled backward kernel, whose prologue then
- *                                   overlaps the fill (not while the stream is being captured into a CUDA graph). */
+ *                                   overlaps the fill (not while the stream is being captured into a CUDA graph).  Default 2
+ *                                   (cfg2 on B200: step 4.186 -> 4.156 ms, decoder-shaped backward 26.7 -> 23.6 us). */
 #define MSDA_KNOB_SLAB          0
 #define MSDA_KNOB_BWD_WIN_ROWS  1
 #define MSDA_KNOB_BWD_LIST_CAP  2

@@ -68,7 +68,7 @@ struct Knobs {
         v[MSDA_KNOB_F32_VEC8_BWD].store(env_int("MSDA_F32_VEC8_BWD", 0));
         v[MSDA_KNOB_BF16_FINE_ROWS].store(env_int("MSDA_BF16_FINE_ROWS", 0));
         v[MSDA_KNOB_BF16_PACKED_FWD].store(env_int("MSDA_BF16_PACKED_FWD", 0));
-        v[MSDA_KNOB_ZERO_FILL].store(env_int("MSDA_ZERO_FILL", 0));
+        v[MSDA_KNOB_ZERO_FILL].store(env_int("MSDA_ZERO_FILL", 2));   // measured: profiles/r02zy_zero_fill_ab.txt
     }
 };
 Knobs &knobs() { static Knobs k; return k; }
