@@ -55,3 +55,26 @@ def test_missing_library_fails_loudly(tmp_path):
     from uninext_b200 import _cabi
     with pytest.raises(_cabi.MSDALibraryError, match="no CPU / PyTorch fallback"):
         _cabi.load(str(tmp_path / "nope.so"))
+
+
+def test_knob_constants_match_header_and_library(lib_path):
+    """MSDA_KNOB_* of the header == KNOB_* of the ctypes face; msda_set_knob (host-only state, no GPU needed) accepts exactly
+    those indices, reports the documented defaults and restores what it is given."""
+    from uninext_b200 import _cabi
+    text = open(HEADER).read()
+    hdr = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+MSDA_KNOB_(\w+)\s+(\d+)\b", text)}
+    count = hdr.pop("COUNT")
+    assert sorted(hdr.values()) == list(range(count))
+    for name, idx in hdr.items():
+        assert getattr(_cabi, "KNOB_" + name) == idx, name
+    lib = _cabi.load()
+    query = -1000000                                                        # MSDA_KNOB_QUERY
+    assert lib.msda_set_knob(count, query) < 0 and lib.msda_set_knob(-1, query) < 0          # MSDA_E_BADARG
+    if "MSDA_ZERO_FILL" not in os.environ:
+        assert lib.msda_set_knob(_cabi.KNOB_ZERO_FILL, query) == 2         # default: fill kernel as PDL primary (DESIGN 3.5)
+    if "MSDA_SLAB" not in os.environ:
+        assert lib.msda_set_knob(_cabi.KNOB_SLAB, query) == -1             # auto = tiled kernels
+    for idx in range(count):
+        was = lib.msda_set_knob(idx, query)
+        assert lib.msda_set_knob(idx, 7) == was and lib.msda_set_knob(idx, query) == 7
+        assert lib.msda_set_knob(idx, was) == 7 and lib.msda_set_knob(idx, query) == was
