@@ -126,3 +126,26 @@ def test_workload_shapes_match_survey_table():
     assert CONFIGS["cfg1"].S == 2125 and CONFIGS["cfg3"].S == 32640 and CONFIGS["cfg4"].S == 5100
     assert algorithmic_bytes(c2, "enc", 4, "fwd") == 160011264            # 28 B / sample
     assert algorithmic_bytes(c2, "enc", 4, "bwd") == 320022528            # 56 B / sample
+
+
+def test_level_table_is_validated_once_per_distinct_table():
+    """`MSDeformAttn` keeps the reference's `(H_l * W_l).sum() == Len_in` assertion (ms_deform_attn.py:91) but pays its
+    device->host read once per distinct table: cached on (storage, version), re-checked after an in-place change."""
+    from uninext_b200.modules import ms_deform_attn as mod
+    ss = torch.tensor([[4, 5], [2, 3]])
+    lsi = torch.tensor([0, 20])
+    mod._LEVELS_OK.clear()
+    mod.check_levels(ss, lsi, 26)
+    assert len(mod._LEVELS_OK) == 1
+    mod.check_levels(ss, lsi, 26)                                           # cache hit: no new entry
+    assert len(mod._LEVELS_OK) == 1
+    with pytest.raises(AssertionError, match="Len_in"):
+        mod.check_levels(ss, lsi, 27)                                       # same table, other flattened length
+    with pytest.raises(AssertionError, match="level_start_index"):
+        mod.check_levels(ss, torch.tensor([0, 19]), 26)
+    with pytest.raises(AssertionError, match="positive"):
+        mod.check_levels(torch.tensor([[4, 5], [0, 3]]), None, 20)          # an empty level would index row -1
+    ss[1, 1] = 4                                                            # in-place edit bumps the version counter
+    with pytest.raises(AssertionError, match="Len_in"):
+        mod.check_levels(ss, lsi, 26)
+    mod.check_levels(ss, lsi, 28)
